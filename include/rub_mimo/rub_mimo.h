@@ -1,0 +1,296 @@
+/*
+ * rub_mimo.h — C ABI of librubmimo_b200.so, the B200-native MIMO-OFDM receive path.
+ *
+ * The reference (yefeng22222/RUB_MIMO) has no FFI/plugin layer: its boundary is the C++
+ * class API of mimo/framing.h.  This header is the C-ABI a maintainer binds instead of
+ * linking mimo/framing.cc; every entry point cites the reference interface it replaces.
+ * A framing.h-compatible C++ facade on top of this ABI is in include/rub_mimo/framing.h.
+ *
+ * Conventions
+ *   - All complex samples are interleaved float32 (re, im) = the reference's gr_complex
+ *     (mimo/framing.h:23, std::complex<float>).
+ *   - No exceptions, no exit(): every call returns a rub_status (the reference uses
+ *     assert/printf/exit(1), mimo/framing.cc:395-401, :498-499, :1021-1022).
+ *   - Device entry points take raw CUDA device pointers and run asynchronously on the
+ *     handle's CUDA stream.  There is NO CPU fallback: without a CUDA device the device
+ *     entry points return RUB_ERR_NO_DEVICE.
+ *   - One host thread per handle (the reference objects are single-threaded,
+ *     mimo/main.cc:922).
+ */
+#ifndef RUB_MIMO_H
+#define RUB_MIMO_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RUB_ABI_VERSION 1u
+
+/* ---------------------------------------------------------------- status ----------- */
+typedef enum rub_status {
+  RUB_OK = 0,
+  RUB_ERR_INVALID_ARG = 1,   /* bad pointer / size / enum                               */
+  RUB_ERR_UNSUPPORTED = 2,   /* legal config this build has no kernel for               */
+  RUB_ERR_NO_DEVICE = 3,     /* no CUDA device: the receive path has no CPU fallback    */
+  RUB_ERR_CUDA = 4,          /* a CUDA runtime call failed (see rub_last_error)         */
+  RUB_ERR_NOMEM = 5,
+  RUB_ERR_NCCL = 6,
+  RUB_ERR_IO = 7
+} rub_status;
+
+/* ------------------------------------------------------- subcarrier types ---------- */
+/* liquid-dsp OFDMFRAME_SCTYPE_* values used by mimo/framing.cc:218, :312, :949-998.   */
+#define RUB_SCTYPE_NULL 0
+#define RUB_SCTYPE_PILOT 1
+#define RUB_SCTYPE_DATA 2
+
+/* ------------------------------------------------------------ enums ---------------- */
+/* modulation: bits per symbol of a square Gray QAM in liquid-dsp's convention
+ * (replaces MODEM_SCHEME / ARITY, mimo/config.h:107-108; GUI names MOD_QUAM4/16/64,
+ * Interface/usrp_device.h:11-14).                                                     */
+#define RUB_MOD_QPSK 2u
+#define RUB_MOD_QAM16 4u
+#define RUB_MOD_QAM64 6u
+#define RUB_MOD_QAM256 8u
+
+#define RUB_DET_ZF 0u   /* zero forcing (the reference's only detector, framing.cc:1344) */
+#define RUB_DET_MMSE 1u /* W = (G^H G + noise_var I)^-1 G^H                              */
+
+#define RUB_EST_LS_FULLBAND 0u    /* TDMA full-band LS, mimo/framing.cc:801-824          */
+#define RUB_EST_LS_COMB_INTERP 1u /* comb pilots k = t (mod P) + linear interpolation    */
+
+/* flags (quirk switches follow SURVEY.md appendix A numbering)                         */
+#define RUB_FLAG_Q1_IDENTITY_INIT 0x1u /* G accumulates onto identity, framing.cc:302-319 */
+#define RUB_FLAG_MMSE_UNBIASED 0x2u    /* scale MMSE rows by 1/mu_s                       */
+#define RUB_FLAG_ZF_CHOLESKY 0x4u      /* N=2 ZF: use the general Cholesky form instead of
+                                          the reference adjugate form (framing.cc:1352)  */
+
+/* output mask bits for rub_rx_process_batch                                            */
+#define RUB_OUT_EQ 0x1u      /* equalised symbols (what mimo_callback receives)          */
+#define RUB_OUT_LLR 0x2u     /* max-log LLRs                                             */
+#define RUB_OUT_BITS 0x4u    /* packed hard bits                                         */
+#define RUB_OUT_RXDATA 0x8u  /* demodulated symbol indices (rx_data, main.cc:1405)       */
+#define RUB_OUT_G 0x10u      /* channel estimate G                                       */
+
+/* execution path selector (rub_rx_set_path)                                            */
+#define RUB_PATH_AUTO 0u
+#define RUB_PATH_STAGED 1u /* FFT -> HBM -> estimate -> weights -> detect (any config)   */
+#define RUB_PATH_FUSED 2u  /* one persistent kernel per frame batch (eligible configs)   */
+
+/* ------------------------------------------------------------ config --------------- */
+/* Runtime mirror of the compile-time macros of mimo/config.h:65-108.                   */
+typedef struct rub_config {
+  uint32_t struct_size;       /* = sizeof(rub_config), ABI guard                         */
+  uint32_t M;                 /* NUM_SUBCARRIERS (config.h:65), power of two 64..4096    */
+  uint32_t cp_len;            /* CP_LENGTH (config.h:66), <= M                           */
+  uint32_t num_streams;       /* NUM_STREAMS (config.h:106): N = N_tx = N_rx, 1..8       */
+  uint32_t num_access_codes;  /* NUM_ACCESS_CODES (config.h:104)                         */
+  uint32_t num_data_symbols;  /* PID_MAX (config.h:92): payload OFDM symbols per frame   */
+  uint32_t modulation;        /* RUB_MOD_* (bits per symbol)                             */
+  uint32_t detector;          /* RUB_DET_*                                               */
+  uint32_t estimator;         /* RUB_EST_*                                               */
+  uint32_t pilot_spacing;     /* comb spacing P (framing.cc:974 uses 8); 0 -> 8          */
+  uint32_t flags;             /* RUB_FLAG_*                                              */
+  float noise_var;            /* per-subcarrier noise variance in the units of Y         */
+  const uint8_t *sctype;      /* p[M] RUB_SCTYPE_* or NULL = all DATA (USE_ALL_CARRIERS) */
+} rub_config;
+
+/* number of training OFDM symbols per frame: nac*N (full-band TDMA, framing.cc:191-204)
+ * or nac (comb).                                                                       */
+uint32_t rub_config_num_training_symbols(const rub_config *cfg);
+/* M_occupied = M_pilot + M_data (framing.cc:329)                                        */
+uint32_t rub_config_num_occupied(const rub_config *cfg);
+/* validate a configuration; RUB_OK or the reason                                        */
+rub_status rub_config_validate(const rub_config *cfg);
+
+/* batch layout of the IQ input: iq[frame*frame_stride + rx*rx_stride + sample], in
+ * complex samples.  0 = dense ([frame][rx][ (T+D)*(M+cp) ]).                            */
+typedef struct rub_iq_layout {
+  uint64_t frame_stride;
+  uint64_t rx_stride;
+  uint64_t first_sample; /* offset of the first training symbol's CP inside each rx row  */
+} rub_iq_layout;
+
+/* Per-frame outputs (any pointer may be NULL when its RUB_OUT_* bit is clear).
+ *   eq      [frame][stream][sym][j]       complex64   j over occupied carriers, ascending
+ *   llr     [frame][stream][sym][j][bit]  float32     bit 0 = MSB of the symbol index;
+ *                                                     positive => bit 0
+ *   bits    [frame][stream][sym][row]     uint8       row = ceil(Mo*q/8) bytes, MSB first
+ *   rx_data [frame][stream][sym][j]       uint8       liquid-style symbol index
+ *   G       [frame][rx][tx][k]            complex64   all M bins (0 on NULL carriers)
+ *   counters[stream][4] uint64: bit_errors, bits, symbol_errors, symbols
+ *           (accumulated; only touched when tx_data != NULL)
+ * tx_data  [frame][stream][sym][j] uint8  transmitted symbol indices (main.cc:1236)     */
+typedef struct rub_rx_io {
+  const float *iq;
+  rub_iq_layout layout;
+  const uint8_t *tx_data;
+  /* optional per-link FFT window starts (quirk Q2, framing.cc:805-808):
+   * timing[frame][rx][T] int32 sample offsets relative to the rx row start; and
+   * payload_start[frame] (quirk Q4, framing.cc:857).  NULL = pre-aligned frames.        */
+  const int32_t *timing;
+  const int32_t *payload_start;
+  float *eq;
+  float *llr;
+  uint8_t *bits;
+  uint8_t *rx_data;
+  float *G;
+  uint64_t *counters;
+  uint32_t out_mask;
+} rub_rx_io;
+
+/* ------------------------------------------------------- receiver handle ----------- */
+typedef struct rub_rx rub_rx;
+
+/* Replaces rx_beamforming::framesync::framesync (mimo/framing.h:189-196): builds every
+ * table the receive chain needs.  S1 is [tx][code][k] complex64 (the frequency-domain
+ * access codes, framing.cc:1214-1262) or NULL to generate them from the default LFSRs
+ * (rub_default_S1).  device < 0 = current CUDA device.  cuda_stream = a cudaStream_t
+ * (NULL = the handle creates its own non-blocking stream).                              */
+rub_status rub_rx_create(rub_rx **out, const rub_config *cfg, const float *S1, int device,
+                         void *cuda_stream);
+void rub_rx_destroy(rub_rx *h);
+
+/* Replaces framesync::execute's decode work (mimo/framing.cc:535-589, :801-832, and the
+ * demod/count loop mimo/main.cc:1403-1410) for a batch of pre-aligned frames whose IQ
+ * samples are resident in device memory.  Asynchronous on the handle's stream.          */
+rub_status rub_rx_process_batch(rub_rx *h, const rub_rx_io *io, uint32_t n_frames);
+
+/* Same call with HOST buffers (pageable or pinned): copies inputs host->device, runs the
+ * chain, copies the requested outputs back, in chunks pipelined over internal streams.
+ * Synchronous.  This is what the framing.h facade and the offline IQ-file driver call. */
+rub_status rub_rx_process_batch_host(rub_rx *h, const rub_rx_io *io, uint32_t n_frames);
+
+rub_status rub_rx_sync(rub_rx *h);
+rub_status rub_rx_set_path(rub_rx *h, uint32_t path);
+uint32_t rub_rx_get_path(const rub_rx *h);               /* path the last batch used   */
+rub_status rub_rx_reset_counters(rub_rx *h);
+/* device pointer of the internal uint64[4*N] counters (used when io->counters==NULL)    */
+uint64_t *rub_rx_device_counters(rub_rx *h);
+rub_status rub_rx_read_counters(rub_rx *h, uint64_t *host_out /* [4*N] */);
+/* kernels launched by this handle since creation (for bench.py's gpu_launches)          */
+uint64_t rub_rx_launch_count(const rub_rx *h);
+/* CUDA-event time of the last rub_rx_process_batch on the handle's stream, in ms;
+ * requires rub_rx_sync first.  dominant_ms = the detect/fused kernel alone.             */
+rub_status rub_rx_last_timing(rub_rx *h, float *total_ms, float *dominant_ms);
+/* algorithmic bytes of one rub_rx_process_batch call (SURVEY.md 8d formula)             */
+uint64_t rub_rx_algorithmic_bytes(const rub_rx *h, uint32_t n_frames, uint32_t out_mask,
+                                  int with_tx_data);
+
+/* ----------------------------------------------------------- multi-GPU ------------- */
+/* Frames are independent (framing.cc:653-886 recomputes all state per frame), so a batch
+ * is sharded by frame range with no data-path collective; the only exchange is one
+ * ncclAllReduce(sum, uint64) over the 4*N error counters.  NCCL is resolved with dlopen
+ * at first use (no link-time dependency).                                               */
+#define RUB_NCCL_UNIQUE_ID_BYTES 128
+rub_status rub_comm_get_unique_id(uint8_t id[RUB_NCCL_UNIQUE_ID_BYTES]);
+rub_status rub_comm_init(rub_rx *h, const uint8_t id[RUB_NCCL_UNIQUE_ID_BYTES], int rank,
+                         int world_size);
+rub_status rub_allreduce_counters(rub_rx *h); /* in place on the handle's counters      */
+rub_status rub_comm_destroy(rub_rx *h);
+/* frame range [begin, end) of `rank` when n_frames are sharded over world_size ranks    */
+void rub_shard_range(uint64_t n_frames, int rank, int world_size, uint64_t *begin,
+                     uint64_t *end);
+
+/* ------------------------------------------ host-only setup (a8 / a9 rows) --------- */
+/* liquid-dsp msequence stand-in (Fibonacci LFSR, liquid <= 1.3 semantics) used at
+ * mimo/main.cc:1268-1270, mimo/framing.cc:1075, :1240.                                  */
+typedef struct rub_msequence {
+  uint32_t m, g, a, n, v, b;
+} rub_msequence;
+void rub_msequence_init(rub_msequence *ms, uint32_t m, uint32_t g, uint32_t a);
+void rub_msequence_reset(rub_msequence *ms);
+uint32_t rub_msequence_advance(rub_msequence *ms);
+uint32_t rub_msequence_generate_symbol(rub_msequence *ms, uint32_t bps);
+
+/* mimo/framing.cc:949-998; use_all_carriers/add_null_carriers mirror config.h:95-96     */
+void rub_ofdmframe_init_default_sctype(uint8_t *p, uint32_t M, int use_all_carriers,
+                                       int add_null_carriers);
+/* mimo/framing.cc:1000-1030 (returns RUB_ERR_INVALID_ARG instead of exit(1))            */
+rub_status rub_ofdmframe_validate_sctype(const uint8_t *p, uint32_t M, uint32_t *M_null,
+                                         uint32_t *M_pilot, uint32_t *M_data);
+/* mimo/framing.cc:1053-1111 (USE_NEW_INIT_S0)                                            */
+rub_status rub_ofdmframe_init_S0(const uint8_t *p, uint32_t M, float *S0, float *s0,
+                                 rub_msequence *ms);
+/* mimo/framing.cc:1214-1262 (USE_NEW_INIT_S1, BPSK)                                      */
+rub_status rub_ofdmframe_init_S1(const uint8_t *p, uint32_t M, uint32_t num_access_codes,
+                                 float *S1, float *s1, rub_msequence *ms);
+/* S1 for all N streams from the default generator polynomials (config.h:70-75 for
+ * streams 0/1, further degree-13 primitive polynomials for streams 2..7).
+ * S1 [N][nac][M] complex64, s1 (time domain, may be NULL) same shape.                   */
+rub_status rub_default_S1(const rub_config *cfg, float *S1, float *s1);
+rub_status rub_default_S0(const rub_config *cfg, float *S0, float *s0);
+uint32_t rub_default_lfsr_poly(uint32_t stream);
+
+/* mimo/framing.cc:1344-1367: 2x2 adjugate "inverse"; W, G row-major [2][2] complex64;
+ * returns 1/|det|^2 in *gain.                                                            */
+rub_status rub_invert_2x2(float *W, const float *G, float *gain);
+
+/* liquid-dsp square-QAM modem in the convention of SURVEY.md 8c (replaces
+ * modem_modulate / modem_demodulate, mimo/main.cc:1237, :1405).                         */
+rub_status rub_modem_modulate(uint32_t bits_per_symbol, uint32_t sym, float out[2]);
+rub_status rub_modem_demodulate(uint32_t bits_per_symbol, const float in[2], uint32_t *sym);
+
+/* ------------------------------------------------------- frame generator ----------- */
+/* Replaces rx_beamforming::framegen (mimo/framing.h:42-103).                            */
+typedef struct rub_framegen rub_framegen;
+rub_status rub_framegen_create(rub_framegen **out, const rub_config *cfg, const float *S0,
+                               const float *s0, const float *s1 /* [N][nac][M] */);
+void rub_framegen_destroy(rub_framegen *fg);
+/* framegen::write_sync_words (framing.cc:169-208): tx_buff[stream] each
+ * (nac*N+1)*(M+cp) complex; returns the sample count.                                   */
+uint32_t rub_framegen_write_sync_words(rub_framegen *fg, float *const *tx_buff);
+/* comb-pilot training symbols for RUB_EST_LS_COMB_INTERP: nac symbols, all tx active on
+ * disjoint combs.  tx_buff[stream] each nac*(M+cp) complex.                             */
+uint32_t rub_framegen_write_comb_words(rub_framegen *fg, float *const *tx_buff);
+/* framegen::assemble_mimo_packet (framing.cc:210-235): in_buff[stream] has Mo symbols,
+ * tx_buff[stream] receives M+cp samples; returns symbol_len.                            */
+uint32_t rub_framegen_assemble_mimo_packet(rub_framegen *fg, float *const *tx_buff,
+                                           const float *const *in_buff);
+
+/* --------------------------------------------- synthetic / offline IQ source -------- */
+/* Replaces the USRP stream (mimo/main.cc:872-898) with a synthetic source: for each
+ * frame, random symbol indices -> modulate -> framegen -> BASEBAND_GAIN -> per-link
+ * L-tap Rayleigh (or a fixed flat channel) -> AWGN, written pre-aligned in the batch
+ * layout.  Counter-based RNG keyed by (seed, global frame index) so any frame can be
+ * regenerated independently (results do not depend on how frames are sharded).          */
+typedef struct rub_synth_params {
+  uint64_t seed;
+  uint64_t first_frame;   /* global index of frame 0 of this call                       */
+  uint32_t n_taps;        /* channel taps per link, each CN(0, 1/n_taps); 0 = fixed_H   */
+  float snr_db;           /* per-rx SNR (signal power measured through the channel)      */
+  float baseband_gain;    /* BASEBAND_GAIN, config.h:59                                  */
+  const float *fixed_H;   /* [rx][tx] complex64 flat channel when n_taps == 0           */
+  uint32_t include_s0;    /* prepend zeros + S0 like the reference burst (appendix C)   */
+  uint32_t lead_zeros;    /* leading zero samples when include_s0                       */
+  uint32_t n_threads;     /* host threads (0 = all)                                     */
+} rub_synth_params;
+/* samples per rx row the generator writes for one frame                                 */
+uint64_t rub_synth_row_samples(const rub_config *cfg, const rub_synth_params *sp);
+/* noise variance per subcarrier (units of Y) the generator used for `snr_db`            */
+rub_status rub_synth_frames(const rub_config *cfg, const rub_synth_params *sp,
+                            const float *S0s0 /* NULL=default */, const float *S1,
+                            const float *s1, uint32_t n_frames, float *iq /* host */,
+                            uint8_t *tx_data /* host, may be NULL */,
+                            float *noise_var_out /* may be NULL */);
+
+/* on-disk formats of the reference (mimo/main.cc:831-833, :906-918, :1243-1262,
+ * :1413-1419; documented by mimo/apps/plot.py:27-40): raw fc32 / uint32 / float32.      */
+rub_status rub_file_read_fc32(const char *path, float *dst, uint64_t max_samples,
+                              uint64_t *n_read);
+rub_status rub_file_write_fc32(const char *path, const float *src, uint64_t n_samples);
+rub_status rub_file_write_u32(const char *path, const uint32_t *src, uint64_t n);
+
+/* ------------------------------------------------------------- misc ---------------- */
+const char *rub_strerror(rub_status s);
+const char *rub_last_error(void); /* thread-local detail string of the last failure     */
+uint32_t rub_abi_version(void);
+int rub_device_count(void);       /* 0 when no CUDA device is visible                   */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RUB_MIMO_H */

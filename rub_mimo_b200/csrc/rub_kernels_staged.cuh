@@ -1,0 +1,264 @@
+// rub_kernels_staged.cuh — the staged receive path: FFT -> Y (HBM) -> LS estimate -> weights ->
+// detect/demap.  Works for every supported configuration (any N <= 8, M <= 4096, ragged
+// carrier allocations, per-link timing tables) and is the fallback for configurations the
+// fused kernel (rub_kernels_fused.cuh) is not eligible for.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "rub_internal.h"
+
+namespace rub {
+
+struct ChainArgs {
+  // input
+  const cf *iq;
+  unsigned long long frame_stride, rx_stride, first_sample;
+  const int *timing;         // [frame][rx][T] or null
+  const int *payload_start;  // [frame] or null
+  // geometry
+  int M, cp, L, N, nac, D, T, Mo, q, P, n_frames, row_bytes;
+  float dn, s_ls;
+  unsigned flags;
+  int estimator;
+  // tables
+  const cf *tw;            // packed stage twiddles
+  const unsigned short *occ;  // j -> k
+  const float *sgn;        // [tx][code][k] in {-1,0,+1}
+  const unsigned char *scnull;  // [k] 1 = null carrier
+  // scratch / outputs
+  cf *Y;       // [frame][sym][rx][k]
+  cf *G;       // [frame][rx][tx][k]
+  cf *W;       // [frame][stream][rx][k]
+  float *gain; // [frame][stream][k]
+  float *isig; // [frame][stream][k]
+  cf *eq;
+  float *llr;
+  unsigned char *bits;
+  unsigned char *rx_data;
+  const unsigned char *tx_data;
+  unsigned long long *counters;
+};
+
+__device__ __forceinline__ long long window_start(const ChainArgs &a, int frame, int r, int sym) {
+  if (sym < a.T) {
+    if (a.timing) return a.timing[((long long)frame * a.N + r) * a.T + sym];
+    return (long long)a.first_sample + (long long)sym * a.L + a.cp;
+  }
+  const long long pay0 = a.payload_start ? (long long)a.payload_start[frame]
+                                         : (long long)a.first_sample + (long long)a.T * a.L;
+  return pay0 + (long long)(sym - a.T) * a.L + a.cp;
+}
+
+// ---- K1: batched CP-strip + FFT (+ 1/sqrt(Mo) scale on payload symbols) -----------------
+// CTA = F FFTs x NT threads; stage 0 reads the M window samples straight from HBM (coalesced
+// 8-byte loads, the cp prefix is simply never touched), later stages ping-pong in smem.
+template <int LOG2M, int F>
+__global__ void __launch_bounds__(FftPlan<LOG2M>::NT *F) k_fft_staged(ChainArgs a) {
+  using FF = Fft<LOG2M>;
+  using PL = FftPlan<LOG2M>;
+  using TW = FftTw<LOG2M>;
+  constexpr int NT = FF::NT, M = FF::M, PAD = fft_padded_size(M);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  cf *smem = reinterpret_cast<cf *>(smem_raw);
+  const int slot = threadIdx.x / NT, tid = threadIdx.x % NT;
+  const long long nsym = a.T + a.D;
+  const long long total = (long long)a.n_frames * nsym * a.N;
+  long long fid = (long long)blockIdx.x * F + slot;
+  const bool valid = fid < total;
+  if (!valid) fid = total - 1;
+  const int r = (int)(fid % a.N);
+  const int sym = (int)((fid / a.N) % nsym);
+  const int frame = (int)(fid / (a.N * nsym));
+  const cf *in = a.iq + (long long)frame * a.frame_stride + (long long)r * a.rx_stride +
+                 window_start(a, frame, r, sym);
+  cf *out = a.Y + fid * M;
+  const float scale = sym >= a.T ? a.dn : 1.0f;
+  cf *A = smem + (size_t)slot * 2 * PAD, *B = A + PAD;
+  cf v[FF::PTS];
+  FF::S0::template load<false>(tid, in, v);
+  FF::S0::compute(tid, v, nullptr);
+  FF::S0::template store<true, false>(tid, v, A, 1.f);
+  __syncthreads();
+  FF::S1::template load<true>(tid, A, v);
+  FF::S1::compute(tid, v, a.tw + TW::OFF1);
+  if (PL::NSTG == 2) {
+    if (valid) FF::S1::template store<false, true>(tid, v, out, scale);
+  } else {
+    FF::S1::template store<true, false>(tid, v, B, 1.f);
+    __syncthreads();
+    FF::S2::template load<true>(tid, B, v);
+    FF::S2::compute(tid, v, a.tw + TW::OFF2);
+    if (valid) FF::S2::template store<false, true>(tid, v, out, scale);
+  }
+}
+
+// ---- K2: LS channel estimate (mimo/framing.cc:801-824) ---------------------------------
+// thread per (frame, rx, tx, k)
+__global__ void k_ls_fullband(ChainArgs a) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)a.n_frames * a.N * a.N * a.M;
+  if (i >= total) return;
+  const int k = (int)(i % a.M);
+  const int t = (int)((i / a.M) % a.N);
+  const int r = (int)((i / ((long long)a.M * a.N)) % a.N);
+  const int frame = (int)(i / ((long long)a.M * a.N * a.N));
+  const bool nul = a.scnull[k];
+  // quirk Q1: G starts as identity on non-null carriers (framing.cc:302-319)
+  cf acc = mk(((a.flags & RUB_FLAG_Q1_IDENTITY_INIT) && r == t && !nul) ? 1.0f : 0.0f, 0.f);
+  if (!nul) {
+    const long long nsym = a.T + a.D;
+    for (int c = 0; c < a.nac; c++) {
+      const int ts = c * a.N + t;
+      const cf X = a.Y[(((long long)frame * nsym + ts) * a.N + r) * a.M + k];
+      const float s = a.sgn[((long long)t * a.nac + c) * a.M + k];
+      acc.x = acc.x + X.x * s;  // X / S1 with S1 = +-1: exact sign flip
+      acc.y = acc.y + X.y * s;
+    }
+  }
+  a.G[i] = cscale(acc, a.s_ls);
+}
+
+// comb pilots k = t (mod P) + linear interpolation, hold at the band edges
+__device__ __forceinline__ cf comb_pilot(const ChainArgs &a, int frame, int r, int t, int kp) {
+  cf acc = mk(((a.flags & RUB_FLAG_Q1_IDENTITY_INIT) && r == t) ? 1.0f : 0.0f, 0.f);
+  const long long nsym = a.T + a.D;
+  for (int c = 0; c < a.nac; c++) {
+    const cf X = a.Y[(((long long)frame * nsym + c) * a.N + r) * a.M + kp];
+    const float s = a.sgn[((long long)t * a.nac + c) * a.M + kp];
+    acc.x = acc.x + X.x * s;
+    acc.y = acc.y + X.y * s;
+  }
+  return cscale(acc, a.s_ls);
+}
+__global__ void k_ls_comb(ChainArgs a) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)a.n_frames * a.N * a.N * a.M;
+  if (i >= total) return;
+  const int k = (int)(i % a.M);
+  const int t = (int)((i / a.M) % a.N);
+  const int r = (int)((i / ((long long)a.M * a.N)) % a.N);
+  const int frame = (int)(i / ((long long)a.M * a.N * a.N));
+  const int P = a.P, last = t + (a.M / P - 1) * P;
+  cf g;
+  if (k % P == t) g = comb_pilot(a, frame, r, t, k);
+  else if (k < t) g = comb_pilot(a, frame, r, t, t);
+  else if (k > last) g = comb_pilot(a, frame, r, t, last);
+  else {
+    const int k0 = t + ((k - t) / P) * P;
+    const cf ga = comb_pilot(a, frame, r, t, k0), gb = comb_pilot(a, frame, r, t, k0 + P);
+    const float f = (float)(k - k0) * (1.0f / (float)P);
+    g = mk(fmaf(f, gb.x - ga.x, ga.x), fmaf(f, gb.y - ga.y, ga.y));
+  }
+  a.G[i] = g;
+}
+
+// ---- K3: per-subcarrier ZF / MMSE weights (mimo/framing.cc:826-832, :1344-1367) ---------
+template <int N>
+__global__ void k_weights(ChainArgs a, WeightMode wm) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)a.n_frames * a.M;
+  if (i >= total) return;
+  const int k = (int)(i % a.M);
+  const long long frame = i / a.M;
+  const cf *Gf = a.G + frame * N * N * a.M;
+  cf *Wf = a.W + frame * N * N * a.M;
+  float *gf = a.gain + frame * N * a.M, *sf = a.isig + frame * N * a.M;
+  if (a.scnull[k]) {
+#pragma unroll
+    for (int e = 0; e < N * N; e++) Wf[(long long)e * a.M + k] = mk(0.f, 0.f);
+#pragma unroll
+    for (int s = 0; s < N; s++) { gf[(long long)s * a.M + k] = 0.f; sf[(long long)s * a.M + k] = 0.f; }
+    return;
+  }
+  cf G[N * N], W[N * N];
+  float gain[N], isig[N];
+#pragma unroll
+  for (int e = 0; e < N * N; e++) G[e] = Gf[(long long)e * a.M + k];
+  compute_weights<N>(wm, G, W, gain, isig);
+#pragma unroll
+  for (int e = 0; e < N * N; e++) Wf[(long long)e * a.M + k] = W[e];
+#pragma unroll
+  for (int s = 0; s < N; s++) { gf[(long long)s * a.M + k] = gain[s]; sf[(long long)s * a.M + k] = isig[s]; }
+}
+
+// ---- K4: detect + demap + count (mimo/framing.cc:569-586, mimo/main.cc:1403-1410) --------
+// blockIdx.x = (frame, symbol, stream); each thread owns 8 consecutive occupied carriers so
+// its packed hard bits are whole bytes for every modulation.
+template <int N>
+__global__ void __launch_bounds__(128) k_detect(ChainArgs a, DemapLut lutp) {
+  __shared__ DemapLut lut;
+  __shared__ unsigned long long red[3];
+  if (threadIdx.x == 0) { lut = lutp; red[0] = red[1] = red[2] = 0; }
+  __syncthreads();
+  const int s = blockIdx.x % N;
+  const int d = (blockIdx.x / N) % a.D;
+  const long long frame = blockIdx.x / (N * a.D);
+  const int jg = blockIdx.y * blockDim.x + threadIdx.x;
+  const int m = lut.m, q = a.q, PL = 1 << m;
+  const float alpha = lut.alpha;
+  const long long nsym = a.T + a.D;
+  const cf *Yf = a.Y + ((frame * nsym + a.T + d) * N) * a.M;
+  const cf *Wf = a.W + (frame * N * N + (long long)s * N) * a.M;
+  const float *gf = a.gain + (frame * N + s) * a.M, *sf = a.isig + (frame * N + s) * a.M;
+  const long long orow = ((frame * N + s) * a.D + d);
+  unsigned long long word = 0;
+  unsigned be = 0, se = 0, ns = 0;
+  const int j0 = jg * 8;
+  for (int u = 0; u < 8; u++) {
+    const int j = j0 + u;
+    if (j >= a.Mo) break;
+    const int k = a.occ[j];
+    cf acc = mk(0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < N; r++) acc = cmac(acc, Wf[(long long)r * a.M + k], Yf[(long long)r * a.M + k]);
+    const cf z = cscale(acc, gf[k]);
+    const unsigned si = slice_axis_rt(z.x, m, alpha), sq = slice_axis_rt(z.y, m, alpha);
+    const unsigned sym = (gray_encode(si) << m) + gray_encode(sq);
+    const long long o = orow * a.Mo + j;
+    if (a.eq) a.eq[o] = z;
+    if (a.rx_data) a.rx_data[o] = (unsigned char)sym;
+    if (a.llr) {
+      const float is = sf[k];
+      float *lp = a.llr + o * q;
+      for (int b = 0; b < m; b++) {
+        lp[b] = fmaf(lut.slope[b * PL + si], z.x, lut.icpt[b * PL + si]) * is;
+        lp[m + b] = fmaf(lut.slope[b * PL + sq], z.y, lut.icpt[b * PL + sq]) * is;
+      }
+    }
+    word = (word << q) | sym;
+    ns++;
+    if (a.tx_data) {
+      const unsigned ts = a.tx_data[o];
+      be += __popc(ts ^ sym);
+      se += (ts != sym);
+    }
+  }
+  if (a.bits && ns) {
+    const int nbits = ns * q, nbytes = (nbits + 7) / 8;
+    word <<= (64 - nbits);
+    unsigned char *bp = a.bits + orow * a.row_bytes + (long long)jg * q;
+    for (int i = 0; i < nbytes; i++) bp[i] = (unsigned char)(word >> (56 - 8 * i));
+  }
+  if (a.tx_data && a.counters) {
+    // warp reduce, then one shared atomic per warp, one global atomic per CTA and counter
+    for (int off = 16; off; off >>= 1) {
+      be += __shfl_xor_sync(0xffffffffu, be, off);
+      se += __shfl_xor_sync(0xffffffffu, se, off);
+      ns += __shfl_xor_sync(0xffffffffu, ns, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(&red[0], (unsigned long long)be);
+      atomicAdd(&red[1], (unsigned long long)se);
+      atomicAdd(&red[2], (unsigned long long)ns);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && red[2]) {
+      atomicAdd(&a.counters[s * 4 + 0], red[0]);
+      atomicAdd(&a.counters[s * 4 + 1], red[2] * (unsigned long long)q);
+      atomicAdd(&a.counters[s * 4 + 2], red[1]);
+      atomicAdd(&a.counters[s * 4 + 3], red[2]);
+    }
+  }
+}
+
+}  // namespace rub

@@ -1,0 +1,607 @@
+// rub_rx.cu — receiver handle, kernel dispatch and the device-side C ABI of
+// librubmimo_b200.so (include/rub_mimo/rub_mimo.h).  There is no CPU execution path in this
+// file: without a CUDA device every entry point returns RUB_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "rub_internal.h"
+#include "rub_kernels_fused.cuh"
+#include "rub_kernels_staged.cuh"
+
+using namespace rub;
+
+#define CUDA_TRY(x)                                                                       \
+  do {                                                                                    \
+    cudaError_t e_ = (x);                                                                 \
+    if (e_ != cudaSuccess) {                                                              \
+      set_error("%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return RUB_ERR_CUDA;                                                                \
+    }                                                                                     \
+  } while (0)
+
+// ---------------------------------------------------------------- NCCL via dlopen -----
+typedef struct { char internal[128]; } nccl_uid;
+typedef int (*fn_ncclGetUniqueId)(nccl_uid *);
+typedef int (*fn_ncclCommInitRank)(void **, int, nccl_uid, int);
+typedef int (*fn_ncclAllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*fn_ncclCommDestroy)(void *);
+typedef const char *(*fn_ncclGetErrorString)(int);
+static struct {
+  void *lib;
+  fn_ncclGetUniqueId GetUniqueId;
+  fn_ncclCommInitRank CommInitRank;
+  fn_ncclAllReduce AllReduce;
+  fn_ncclCommDestroy CommDestroy;
+  fn_ncclGetErrorString GetErrorString;
+} g_nccl;
+static rub_status nccl_load() {
+  if (g_nccl.lib) return RUB_OK;
+  void *l = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!l) l = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!l) { set_error("cannot load libnccl.so.2: %s", dlerror()); return RUB_ERR_NCCL; }
+  g_nccl.GetUniqueId = (fn_ncclGetUniqueId)dlsym(l, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (fn_ncclCommInitRank)dlsym(l, "ncclCommInitRank");
+  g_nccl.AllReduce = (fn_ncclAllReduce)dlsym(l, "ncclAllReduce");
+  g_nccl.CommDestroy = (fn_ncclCommDestroy)dlsym(l, "ncclCommDestroy");
+  g_nccl.GetErrorString = (fn_ncclGetErrorString)dlsym(l, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
+    set_error("libnccl.so.2 lacks a required symbol");
+    return RUB_ERR_NCCL;
+  }
+  g_nccl.lib = l;
+  return RUB_OK;
+}
+
+// ---------------------------------------------------------------- handle --------------
+struct rub_rx {
+  HostCfg h;
+  int device = 0;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  // tables
+  cf *d_tw = nullptr;
+  unsigned short *d_occ = nullptr;
+  float *d_sgn = nullptr;
+  unsigned char *d_null = nullptr;
+  DemapLut lut;
+  WeightMode wm;
+  // staged scratch
+  void *d_scratch = nullptr;
+  size_t scratch_bytes = 0;
+  // fused scratch
+  cf *d_fW = nullptr;
+  float *d_fG = nullptr;
+  int fused_grid = 0;
+  size_t fused_smem = 0;
+  bool fused_ready = false;
+  uint64_t *d_counters = nullptr;
+  uint32_t path = RUB_PATH_AUTO, last_path = 0;
+  uint64_t launches = 0;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool timed = false;
+  // host pipeline
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  void *d_pipe = nullptr;
+  size_t pipe_bytes = 0;
+  cudaEvent_t pev[12] = {};
+  // comm
+  void *comm = nullptr;
+  int rank = 0, world = 1;
+};
+
+template <int LOG2M, int N>
+static rub_status fused_prepare(rub_rx *h, size_t *smem_out, int *grid_out) {
+  using TR = FusedTraits<LOG2M, N>;
+  const size_t smem = TR::smem_bytes((int)h->h.q);
+  CUDA_TRY(cudaFuncSetAttribute(k_rx_fused<LOG2M, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_rx_fused<LOG2M, N>, TR::THREADS, smem));
+  if (occ < 1) { set_error("fused kernel does not fit (smem %zu B)", smem); return RUB_ERR_UNSUPPORTED; }
+  *smem_out = smem;
+  *grid_out = occ * h->num_sms;
+  return RUB_OK;
+}
+template <int LOG2M, int N>
+static void fused_launch(int grid, size_t smem, cudaStream_t st, const FusedArgs &fa, const DemapLut &lut) {
+  k_rx_fused<LOG2M, N><<<grid, FusedTraits<LOG2M, N>::THREADS, smem, st>>>(fa, lut);
+}
+
+// the (log2 M, N) pairs the fused kernel is instantiated for
+#define RUB_FUSED_LIST(X) X(9, 2) X(9, 4) X(10, 2) X(10, 4) X(11, 1) X(11, 2) X(11, 4) X(12, 1) X(12, 2)
+
+static bool fused_has_instance(uint32_t l2, uint32_t N) {
+#define X(L, NN) if (l2 == L && N == NN) return true;
+  RUB_FUSED_LIST(X)
+#undef X
+  return false;
+}
+static rub_status fused_prepare_dispatch(rub_rx *h, size_t *smem, int *grid) {
+#define X(L, NN) if (h->h.log2M == L && h->h.N == NN) return fused_prepare<L, NN>(h, smem, grid);
+  RUB_FUSED_LIST(X)
+#undef X
+  return RUB_ERR_UNSUPPORTED;
+}
+static void fused_launch_dispatch(rub_rx *h, int grid, size_t smem, const FusedArgs &fa) {
+#define X(L, NN) if (h->h.log2M == L && h->h.N == NN) { fused_launch<L, NN>(grid, smem, h->stream, fa, h->lut); return; }
+  RUB_FUSED_LIST(X)
+#undef X
+}
+
+// is the fused kernel applicable to this configuration + call?
+static bool fused_eligible(const rub_rx *h, const rub_rx_io *io, uint64_t frame_stride, uint64_t rx_stride) {
+  const HostCfg &c = h->h;
+  if (!fused_has_instance(c.log2M, c.N)) return false;
+  if (c.Mo != c.M) return false;                                   // ragged allocations -> staged
+  if (c.c.estimator != RUB_EST_LS_FULLBAND) return false;          // comb -> staged
+  if (io->timing || io->payload_start) return false;               // per-link windows -> staged
+  // cp.async.bulk needs 16-byte aligned sources: even sample offsets everywhere
+  if ((c.cp | c.L | io->layout.first_sample | frame_stride | rx_stride) & 1) return false;
+  if (((uintptr_t)io->iq & 15) || ((uintptr_t)io->llr & 15) || ((uintptr_t)io->bits & 15) || ((uintptr_t)io->eq & 15)) return false;
+  if (((uintptr_t)io->rx_data & 1) || ((uintptr_t)io->tx_data & 1)) return false;
+  return true;
+}
+
+static void fill_weight_mode(rub_rx *h) {
+  const HostCfg &c = h->h;
+  h->wm.nv = c.c.noise_var;
+  h->wm.mmse = (c.c.detector == RUB_DET_MMSE && c.c.noise_var > 0.f) ? 1 : 0;
+  h->wm.unbiased = (c.c.flags & RUB_FLAG_MMSE_UNBIASED) ? 1 : 0;
+  h->wm.zf2_adjugate = (c.N == 2 && c.c.detector == RUB_DET_ZF && !(c.c.flags & RUB_FLAG_ZF_CHOLESKY)) ? 1 : 0;
+}
+
+extern "C" int rub_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+extern "C" rub_status rub_rx_create(rub_rx **out, const rub_config *cfg, const float *S1, int device, void *cuda_stream) {
+  if (!out) { set_error("out is NULL"); return RUB_ERR_INVALID_ARG; }
+  *out = nullptr;
+  rub_rx *h = new rub_rx();
+  rub_status st = host_cfg_init(h->h, cfg);
+  if (st) { delete h; return st; }
+  if (rub_device_count() < 1) {
+    delete h;
+    set_error("no CUDA device visible: librubmimo_b200 has no CPU fallback for the receive path");
+    return RUB_ERR_NO_DEVICE;
+  }
+  const HostCfg &c = h->h;
+  if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+  h->device = device;
+#define CT(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { set_error("%s failed: %s", #x, cudaGetErrorString(e_)); rub_rx_destroy(h); return RUB_ERR_CUDA; } } while (0)
+  CT(cudaSetDevice(device));
+  CT(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
+  if (cuda_stream) h->stream = (cudaStream_t)cuda_stream;
+  else { CT(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+  for (int i = 0; i < 4; i++) CT(cudaEventCreate(&h->ev[i]));
+  // tables
+  std::vector<cf> master, packed;
+  build_twiddles(c.log2M, master, packed);
+  CT(cudaMalloc(&h->d_tw, sizeof(cf) * packed.size()));
+  CT(cudaMemcpy(h->d_tw, packed.data(), sizeof(cf) * packed.size(), cudaMemcpyHostToDevice));
+  std::vector<unsigned short> occ;
+  std::vector<unsigned char> nul(c.M);
+  for (uint32_t k = 0; k < c.M; k++) { nul[k] = c.sctype[k] == RUB_SCTYPE_NULL; if (!nul[k]) occ.push_back((unsigned short)k); }
+  CT(cudaMalloc(&h->d_occ, sizeof(unsigned short) * occ.size()));
+  CT(cudaMemcpy(h->d_occ, occ.data(), sizeof(unsigned short) * occ.size(), cudaMemcpyHostToDevice));
+  CT(cudaMalloc(&h->d_null, c.M));
+  CT(cudaMemcpy(h->d_null, nul.data(), c.M, cudaMemcpyHostToDevice));
+  // access-code signs: S1 is +-1 on occupied carriers (mimo/framing.cc:1240-1248), so X/S1 is a
+  // sign flip; keep only the sign
+  std::vector<float> S1v((size_t)c.N * c.nac * c.M * 2);
+  if (S1) memcpy(S1v.data(), S1, S1v.size() * sizeof(float));
+  else {
+    rub_config c2 = c.c;
+    c2.sctype = c.sctype.data();
+    st = rub_default_S1(&c2, S1v.data(), nullptr);
+    if (st) { rub_rx_destroy(h); return st; }
+  }
+  std::vector<float> sgn((size_t)c.N * c.nac * c.M);
+  for (size_t i = 0; i < sgn.size(); i++) {
+    const float re = S1v[2 * i], im = S1v[2 * i + 1];
+    const bool isnull = nul[i % c.M];
+    if (im != 0.f || (!isnull && re != 1.0f && re != -1.0f)) {
+      set_error("S1 must be BPSK (+-1+0i) on occupied carriers (mimo/framing.cc:1246)");
+      rub_rx_destroy(h);
+      return RUB_ERR_UNSUPPORTED;
+    }
+    sgn[i] = isnull ? 0.f : re;
+  }
+  CT(cudaMalloc(&h->d_sgn, sizeof(float) * sgn.size()));
+  CT(cudaMemcpy(h->d_sgn, sgn.data(), sizeof(float) * sgn.size(), cudaMemcpyHostToDevice));
+  build_demap_lut(c.q, h->lut);
+  fill_weight_mode(h);
+  CT(cudaMalloc(&h->d_counters, sizeof(uint64_t) * 4 * 8));
+  CT(cudaMemset(h->d_counters, 0, sizeof(uint64_t) * 4 * 8));
+#undef CT
+  *out = h;
+  return RUB_OK;
+}
+
+extern "C" void rub_rx_destroy(rub_rx *h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  cudaFree(h->d_tw); cudaFree(h->d_occ); cudaFree(h->d_sgn); cudaFree(h->d_null);
+  cudaFree(h->d_scratch); cudaFree(h->d_fW); cudaFree(h->d_fG); cudaFree(h->d_counters); cudaFree(h->d_pipe);
+  for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+  for (auto &e : h->pev) if (e) cudaEventDestroy(e);
+  if (h->s_in) cudaStreamDestroy(h->s_in);
+  if (h->s_out) cudaStreamDestroy(h->s_out);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+extern "C" rub_status rub_rx_set_path(rub_rx *h, uint32_t path) {
+  if (!h || path > RUB_PATH_FUSED) return RUB_ERR_INVALID_ARG;
+  h->path = path;
+  return RUB_OK;
+}
+extern "C" uint32_t rub_rx_get_path(const rub_rx *h) { return h ? h->last_path : 0; }
+extern "C" uint64_t rub_rx_launch_count(const rub_rx *h) { return h ? h->launches : 0; }
+extern "C" uint64_t *rub_rx_device_counters(rub_rx *h) { return h ? h->d_counters : nullptr; }
+extern "C" rub_status rub_rx_reset_counters(rub_rx *h) {
+  if (!h) return RUB_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMemsetAsync(h->d_counters, 0, sizeof(uint64_t) * 4 * 8, h->stream));
+  return RUB_OK;
+}
+extern "C" rub_status rub_rx_read_counters(rub_rx *h, uint64_t *host_out) {
+  if (!h || !host_out) return RUB_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMemcpyAsync(host_out, h->d_counters, sizeof(uint64_t) * 4 * h->h.N, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return RUB_OK;
+}
+extern "C" rub_status rub_rx_sync(rub_rx *h) {
+  if (!h) return RUB_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return RUB_OK;
+}
+extern "C" rub_status rub_rx_last_timing(rub_rx *h, float *total_ms, float *dominant_ms) {
+  if (!h || !h->timed) { set_error("no timed batch"); return RUB_ERR_INVALID_ARG; }
+  if (total_ms) CUDA_TRY(cudaEventElapsedTime(total_ms, h->ev[0], h->ev[1]));
+  if (dominant_ms) CUDA_TRY(cudaEventElapsedTime(dominant_ms, h->ev[2], h->ev[3]));
+  return RUB_OK;
+}
+
+// Algorithmic (compulsory) HBM bytes of one batch, SURVEY.md 8d:
+//   8*N*(M+cp)*(T+D)                       input samples incl. training symbols
+// + D*N*Mo*(8[eq] + 4q[llr] + q/8[bits] + 1[rx_data] + 1[tx_data])   per-symbol outputs / ref
+// + 8*M*N^2 [G]  + 32*N [counters]
+extern "C" uint64_t rub_rx_algorithmic_bytes(const rub_rx *h, uint32_t n_frames, uint32_t out_mask, int with_tx) {
+  if (!h) return 0;
+  const HostCfg &c = h->h;
+  uint64_t per = 8ull * c.N * c.L * (c.T + c.D);
+  const uint64_t syms = (uint64_t)c.D * c.N * c.Mo;
+  if (out_mask & RUB_OUT_EQ) per += syms * 8;
+  if (out_mask & RUB_OUT_LLR) per += syms * 4 * c.q;
+  if (out_mask & RUB_OUT_BITS) per += (uint64_t)c.D * c.N * c.row_bytes;
+  if (out_mask & RUB_OUT_RXDATA) per += syms;
+  if (with_tx) per += syms;
+  if (out_mask & RUB_OUT_G) per += 8ull * c.M * c.N * c.N;
+  return per * n_frames + (with_tx ? 32ull * c.N : 0);
+}
+
+// ---------------------------------------------------------------- staged dispatch -----
+template <int LOG2M>
+static void launch_fft(const ChainArgs &a, cudaStream_t st, cudaError_t *err) {
+  constexpr int NT = FftPlan<LOG2M>::NT;
+  constexpr int F = NT >= 128 ? 1 : 128 / NT;
+  const size_t smem = (size_t)F * 2 * fft_padded_size(1 << LOG2M) * sizeof(cf);
+  static bool attr_done[16] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_done[dev & 15]) {
+    *err = cudaFuncSetAttribute(k_fft_staged<LOG2M, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (*err != cudaSuccess) return;
+    attr_done[dev & 15] = true;
+  }
+  const long long total = (long long)a.n_frames * (a.T + a.D) * a.N;
+  const unsigned grid = (unsigned)((total + F - 1) / F);
+  k_fft_staged<LOG2M, F><<<grid, NT * F, smem, st>>>(a);
+}
+template <int N>
+static void launch_weights_detect(const ChainArgs &a, const rub_rx *h, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1) {
+  const long long tw = (long long)a.n_frames * a.M;
+  k_weights<N><<<(unsigned)((tw + 127) / 128), 128, 0, st>>>(a, h->wm);
+  if (e0) cudaEventRecord(e0, st);
+  const int groups = (a.Mo + 7) / 8;
+  dim3 grid((unsigned)((long long)a.n_frames * a.D * N), (unsigned)((groups + 127) / 128));
+  k_detect<N><<<grid, 128, 0, st>>>(a, h->lut);
+  if (e1) cudaEventRecord(e1, st);
+}
+
+static rub_status run_staged(rub_rx *h, ChainArgs a, const rub_rx_io *io, uint32_t n_frames, bool timed) {
+  const HostCfg &c = h->h;
+  // per-frame scratch: Y, (G), W, gain, isig
+  const size_t yb = (size_t)(c.T + c.D) * c.N * c.M * sizeof(cf);
+  const size_t gb = (size_t)c.N * c.N * c.M * sizeof(cf);
+  const size_t fb = (size_t)c.N * c.M * sizeof(float);
+  const bool user_G = (io->out_mask & RUB_OUT_G) && io->G;
+  const size_t per_frame = yb + (user_G ? 0 : gb) + gb + 2 * fb;
+  const size_t budget = (size_t)6 << 30;
+  uint32_t chunk = (uint32_t)std::max<size_t>(1, std::min<size_t>(n_frames, budget / per_frame));
+  const size_t need = per_frame * chunk;
+  if (need > h->scratch_bytes) {
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_scratch);
+    h->d_scratch = nullptr;
+    h->scratch_bytes = 0;
+    CUDA_TRY(cudaMalloc(&h->d_scratch, need));
+    h->scratch_bytes = need;
+  }
+  const size_t per_sym = (size_t)c.N * c.D * c.Mo;
+  for (uint32_t f0 = 0; f0 < n_frames; f0 += chunk) {
+    const uint32_t nf = std::min(chunk, n_frames - f0);
+    ChainArgs b = a;
+    b.n_frames = (int)nf;
+    b.iq = a.iq + (size_t)f0 * a.frame_stride;
+    if (a.timing) b.timing = a.timing + (size_t)f0 * c.N * c.T;
+    if (a.payload_start) b.payload_start = a.payload_start + f0;
+    unsigned char *p = (unsigned char *)h->d_scratch;
+    b.Y = (cf *)p; p += yb * nf;
+    if (user_G) b.G = reinterpret_cast<cf *>(io->G) + (size_t)f0 * c.N * c.N * c.M;
+    else { b.G = (cf *)p; p += gb * nf; }
+    b.W = (cf *)p; p += gb * nf;
+    b.gain = (float *)p; p += fb * nf;
+    b.isig = (float *)p;
+    if (a.eq) b.eq = a.eq + f0 * per_sym;
+    if (a.llr) b.llr = a.llr + f0 * per_sym * c.q;
+    if (a.bits) b.bits = a.bits + (size_t)f0 * c.N * c.D * c.row_bytes;
+    if (a.rx_data) b.rx_data = a.rx_data + f0 * per_sym;
+    if (a.tx_data) b.tx_data = a.tx_data + f0 * per_sym;
+    cudaError_t ferr = cudaSuccess;
+    switch (c.log2M) {
+      case 6: launch_fft<6>(b, h->stream, &ferr); break;
+      case 7: launch_fft<7>(b, h->stream, &ferr); break;
+      case 8: launch_fft<8>(b, h->stream, &ferr); break;
+      case 9: launch_fft<9>(b, h->stream, &ferr); break;
+      case 10: launch_fft<10>(b, h->stream, &ferr); break;
+      case 11: launch_fft<11>(b, h->stream, &ferr); break;
+      case 12: launch_fft<12>(b, h->stream, &ferr); break;
+    }
+    CUDA_TRY(ferr);
+    const long long tg = (long long)nf * c.N * c.N * c.M;
+    if (c.c.estimator == RUB_EST_LS_COMB_INTERP) k_ls_comb<<<(unsigned)((tg + 255) / 256), 256, 0, h->stream>>>(b);
+    else k_ls_fullband<<<(unsigned)((tg + 255) / 256), 256, 0, h->stream>>>(b);
+    const bool last = f0 + nf >= n_frames;
+    cudaEvent_t e0 = (timed && last) ? h->ev[2] : nullptr, e1 = (timed && last) ? h->ev[3] : nullptr;
+    switch (c.N) {
+      case 1: launch_weights_detect<1>(b, h, h->stream, e0, e1); break;
+      case 2: launch_weights_detect<2>(b, h, h->stream, e0, e1); break;
+      case 3: launch_weights_detect<3>(b, h, h->stream, e0, e1); break;
+      case 4: launch_weights_detect<4>(b, h, h->stream, e0, e1); break;
+      case 5: launch_weights_detect<5>(b, h, h->stream, e0, e1); break;
+      case 6: launch_weights_detect<6>(b, h, h->stream, e0, e1); break;
+      case 7: launch_weights_detect<7>(b, h, h->stream, e0, e1); break;
+      case 8: launch_weights_detect<8>(b, h, h->stream, e0, e1); break;
+    }
+    h->launches += 4;
+    CUDA_TRY(cudaGetLastError());
+  }
+  h->last_path = RUB_PATH_STAGED;
+  return RUB_OK;
+}
+
+static rub_status run_fused(rub_rx *h, const ChainArgs &a, uint32_t n_frames, bool timed) {
+  const HostCfg &c = h->h;
+  if (!h->fused_ready) {
+    int grid = 0;
+    size_t smem = 0;
+    rub_status st = fused_prepare_dispatch(h, &smem, &grid);
+    if (st) return st;
+    h->fused_grid = grid;
+    h->fused_smem = smem;
+    CUDA_TRY(cudaMalloc(&h->d_fW, (size_t)grid * c.N * c.N * c.M * sizeof(cf)));
+    CUDA_TRY(cudaMalloc(&h->d_fG, (size_t)grid * 2 * c.N * c.M * sizeof(float)));
+    h->fused_ready = true;
+  }
+  const size_t smem = h->fused_smem;
+  FusedArgs fa;
+  fa.a = a;
+  fa.a.n_frames = (int)n_frames;
+  fa.scratchW = h->d_fW;
+  fa.scratchG = h->d_fG;
+  fa.llr_stage_bytes = 256 * (int)c.q;
+  fa.wm = h->wm;
+  const int grid = (int)std::min<uint32_t>((uint32_t)h->fused_grid, n_frames);
+  if (timed) cudaEventRecord(h->ev[2], h->stream);
+  fused_launch_dispatch(h, grid, smem, fa);
+  if (timed) cudaEventRecord(h->ev[3], h->stream);
+  h->launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  h->last_path = RUB_PATH_FUSED;
+  return RUB_OK;
+}
+
+static rub_status process_device(rub_rx *h, const rub_rx_io *io, uint32_t n_frames, bool timed) {
+  if (!h || !io || !io->iq) { set_error("process_batch: NULL argument"); return RUB_ERR_INVALID_ARG; }
+  if (n_frames == 0) return RUB_OK;
+  const HostCfg &c = h->h;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const uint64_t rx_stride = io->layout.rx_stride ? io->layout.rx_stride : (uint64_t)(c.T + c.D) * c.L + io->layout.first_sample;
+  const uint64_t frame_stride = io->layout.frame_stride ? io->layout.frame_stride : rx_stride * c.N;
+  ChainArgs a;
+  memset(&a, 0, sizeof(a));
+  a.iq = reinterpret_cast<const cf *>(io->iq);
+  a.frame_stride = frame_stride; a.rx_stride = rx_stride; a.first_sample = io->layout.first_sample;
+  a.timing = io->timing; a.payload_start = io->payload_start;
+  a.M = c.M; a.cp = c.cp; a.L = c.L; a.N = c.N; a.nac = c.nac; a.D = c.D; a.T = c.T; a.Mo = c.Mo; a.q = c.q; a.P = c.P;
+  a.n_frames = (int)n_frames; a.row_bytes = c.row_bytes;
+  a.dn = c.dn; a.s_ls = c.s_ls; a.flags = c.c.flags; a.estimator = c.c.estimator;
+  a.tw = h->d_tw; a.occ = h->d_occ; a.sgn = h->d_sgn; a.scnull = h->d_null;
+  a.eq = (io->out_mask & RUB_OUT_EQ) ? reinterpret_cast<cf *>(io->eq) : nullptr;
+  a.llr = (io->out_mask & RUB_OUT_LLR) ? io->llr : nullptr;
+  a.bits = (io->out_mask & RUB_OUT_BITS) ? io->bits : nullptr;
+  a.rx_data = (io->out_mask & RUB_OUT_RXDATA) ? io->rx_data : nullptr;
+  a.G = (io->out_mask & RUB_OUT_G) ? reinterpret_cast<cf *>(io->G) : nullptr;
+  a.tx_data = io->tx_data;
+  a.counters = io->counters ? (unsigned long long *)io->counters : (unsigned long long *)h->d_counters;
+  if (((io->out_mask & RUB_OUT_EQ) && !io->eq) || ((io->out_mask & RUB_OUT_LLR) && !io->llr) ||
+      ((io->out_mask & RUB_OUT_BITS) && !io->bits) || ((io->out_mask & RUB_OUT_RXDATA) && !io->rx_data) ||
+      ((io->out_mask & RUB_OUT_G) && !io->G)) {
+    set_error("process_batch: out_mask selects an output whose pointer is NULL");
+    return RUB_ERR_INVALID_ARG;
+  }
+  const bool can_fuse = fused_eligible(h, io, frame_stride, rx_stride);
+  if (h->path == RUB_PATH_FUSED && !can_fuse) {
+    set_error("fused path requested but the configuration / buffers are not eligible");
+    return RUB_ERR_UNSUPPORTED;
+  }
+  const bool use_fused = (h->path == RUB_PATH_FUSED) || (h->path == RUB_PATH_AUTO && can_fuse);
+  if (timed) cudaEventRecord(h->ev[0], h->stream);
+  rub_status st = use_fused ? run_fused(h, a, n_frames, timed) : run_staged(h, a, io, n_frames, timed);
+  if (timed) cudaEventRecord(h->ev[1], h->stream);
+  h->timed = timed && st == RUB_OK;
+  return st;
+}
+
+extern "C" rub_status rub_rx_process_batch(rub_rx *h, const rub_rx_io *io, uint32_t n_frames) {
+  return process_device(h, io, n_frames, true);
+}
+
+// ---------------------------------------------------------------- host-buffer path ----
+// chunked 3-stream pipeline: H2D (s_in) -> chain (handle stream) -> D2H (s_out), two slots
+extern "C" rub_status rub_rx_process_batch_host(rub_rx *h, const rub_rx_io *io, uint32_t n_frames) {
+  if (!h || !io || !io->iq) { set_error("process_batch_host: NULL argument"); return RUB_ERR_INVALID_ARG; }
+  if (io->timing || io->payload_start) {
+    // timing tables are small: run un-pipelined through a temporary device copy
+  }
+  const HostCfg &c = h->h;
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (!h->s_in) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+    for (auto &e : h->pev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  const uint64_t rx_stride = io->layout.rx_stride ? io->layout.rx_stride : (uint64_t)(c.T + c.D) * c.L + io->layout.first_sample;
+  const uint64_t frame_stride = io->layout.frame_stride ? io->layout.frame_stride : rx_stride * c.N;
+  const size_t per_sym = (size_t)c.N * c.D * c.Mo;
+  const size_t in_b = (size_t)frame_stride * sizeof(cf);
+  const size_t eq_b = (io->out_mask & RUB_OUT_EQ) ? per_sym * 8 : 0;
+  const size_t llr_b = (io->out_mask & RUB_OUT_LLR) ? per_sym * 4 * c.q : 0;
+  const size_t bits_b = (io->out_mask & RUB_OUT_BITS) ? (size_t)c.N * c.D * c.row_bytes : 0;
+  const size_t rxd_b = (io->out_mask & RUB_OUT_RXDATA) ? per_sym : 0;
+  const size_t g_b = (io->out_mask & RUB_OUT_G) ? (size_t)c.N * c.N * c.M * 8 : 0;
+  const size_t tx_b = io->tx_data ? per_sym : 0;
+  const size_t tim_b = io->timing ? (size_t)c.N * c.T * 4 : 0;
+  const size_t ps_b = io->payload_start ? 4 : 0;
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t per_frame = in_b + eq_b + llr_b + bits_b + rxd_b + g_b + tx_b + tim_b + ps_b;
+  // chunk sized to ~256 MB of traffic so copies and compute overlap
+  uint32_t chunk = (uint32_t)std::max<size_t>(1, std::min<size_t>(n_frames, ((size_t)256 << 20) / std::max<size_t>(1, per_frame)));
+  const size_t slot_b = al(in_b * chunk) + al(eq_b * chunk) + al(llr_b * chunk) + al(bits_b * chunk) +
+                        al(rxd_b * chunk) + al(g_b * chunk) + al(tx_b * chunk) + al(tim_b * chunk) + al(ps_b * chunk) + 4096;
+  if (2 * slot_b > h->pipe_bytes) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    cudaFree(h->d_pipe);
+    h->d_pipe = nullptr;
+    h->pipe_bytes = 0;
+    CUDA_TRY(cudaMalloc(&h->d_pipe, 2 * slot_b));
+    h->pipe_bytes = 2 * slot_b;
+  }
+  struct Slot { unsigned char *in, *eq, *llr, *bits, *rxd, *g, *tx, *tim, *ps; } sl[2];
+  for (int s = 0; s < 2; s++) {
+    unsigned char *p = (unsigned char *)h->d_pipe + (size_t)s * slot_b;
+    sl[s].in = p; p += al(in_b * chunk);
+    sl[s].eq = p; p += al(eq_b * chunk);
+    sl[s].llr = p; p += al(llr_b * chunk);
+    sl[s].bits = p; p += al(bits_b * chunk);
+    sl[s].rxd = p; p += al(rxd_b * chunk);
+    sl[s].g = p; p += al(g_b * chunk);
+    sl[s].tx = p; p += al(tx_b * chunk);
+    sl[s].tim = p; p += al(tim_b * chunk);
+    sl[s].ps = p;
+  }
+  // pev[0..1] in-done, pev[2..3] compute-done, pev[4..5] out-done (per slot)
+  uint32_t ci = 0;
+  const uint32_t saved_launch_path = h->last_path;
+  (void)saved_launch_path;
+  for (uint32_t f0 = 0; f0 < n_frames; f0 += chunk, ci++) {
+    const uint32_t nf = std::min(chunk, n_frames - f0);
+    const int s = ci & 1;
+    // slot input free once its previous compute is done
+    if (ci >= 2) CUDA_TRY(cudaStreamWaitEvent(h->s_in, h->pev[2 + s], 0));
+    CUDA_TRY(cudaMemcpyAsync(sl[s].in, reinterpret_cast<const cf *>(io->iq) + (size_t)f0 * frame_stride, in_b * nf, cudaMemcpyHostToDevice, h->s_in));
+    if (tx_b) CUDA_TRY(cudaMemcpyAsync(sl[s].tx, io->tx_data + f0 * per_sym, tx_b * nf, cudaMemcpyHostToDevice, h->s_in));
+    if (tim_b) CUDA_TRY(cudaMemcpyAsync(sl[s].tim, io->timing + (size_t)f0 * c.N * c.T, tim_b * nf, cudaMemcpyHostToDevice, h->s_in));
+    if (ps_b) CUDA_TRY(cudaMemcpyAsync(sl[s].ps, io->payload_start + f0, ps_b * nf, cudaMemcpyHostToDevice, h->s_in));
+    CUDA_TRY(cudaEventRecord(h->pev[0 + s], h->s_in));
+    // compute: needs the input, and the slot's previous outputs copied out
+    CUDA_TRY(cudaStreamWaitEvent(h->stream, h->pev[0 + s], 0));
+    if (ci >= 2) CUDA_TRY(cudaStreamWaitEvent(h->stream, h->pev[4 + s], 0));
+    rub_rx_io d = *io;
+    d.iq = (const float *)sl[s].in;
+    d.layout.frame_stride = frame_stride; d.layout.rx_stride = rx_stride;
+    d.tx_data = tx_b ? sl[s].tx : nullptr;
+    d.timing = tim_b ? (const int32_t *)sl[s].tim : nullptr;
+    d.payload_start = ps_b ? (const int32_t *)sl[s].ps : nullptr;
+    d.eq = (float *)sl[s].eq; d.llr = (float *)sl[s].llr; d.bits = sl[s].bits; d.rx_data = sl[s].rxd; d.G = (float *)sl[s].g;
+    d.counters = nullptr;  // accumulate in the handle's device counters
+    rub_status st = process_device(h, &d, nf, false);
+    if (st) return st;
+    CUDA_TRY(cudaEventRecord(h->pev[2 + s], h->stream));
+    // copy out
+    CUDA_TRY(cudaStreamWaitEvent(h->s_out, h->pev[2 + s], 0));
+    if (eq_b) CUDA_TRY(cudaMemcpyAsync(io->eq + (size_t)f0 * per_sym * 2, sl[s].eq, eq_b * nf, cudaMemcpyDeviceToHost, h->s_out));
+    if (llr_b) CUDA_TRY(cudaMemcpyAsync(io->llr + (size_t)f0 * per_sym * c.q, sl[s].llr, llr_b * nf, cudaMemcpyDeviceToHost, h->s_out));
+    if (bits_b) CUDA_TRY(cudaMemcpyAsync(io->bits + (size_t)f0 * c.N * c.D * c.row_bytes, sl[s].bits, bits_b * nf, cudaMemcpyDeviceToHost, h->s_out));
+    if (rxd_b) CUDA_TRY(cudaMemcpyAsync(io->rx_data + (size_t)f0 * per_sym, sl[s].rxd, rxd_b * nf, cudaMemcpyDeviceToHost, h->s_out));
+    if (g_b) CUDA_TRY(cudaMemcpyAsync(io->G + (size_t)f0 * c.N * c.N * c.M * 2, sl[s].g, g_b * nf, cudaMemcpyDeviceToHost, h->s_out));
+    CUDA_TRY(cudaEventRecord(h->pev[4 + s], h->s_out));
+  }
+  CUDA_TRY(cudaStreamSynchronize(h->s_out));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (io->counters) CUDA_TRY(cudaMemcpy(io->counters, h->d_counters, sizeof(uint64_t) * 4 * c.N, cudaMemcpyDeviceToHost));
+  return RUB_OK;
+}
+
+// ---------------------------------------------------------------- multi-GPU ------------
+extern "C" rub_status rub_comm_get_unique_id(uint8_t id[RUB_NCCL_UNIQUE_ID_BYTES]) {
+  rub_status st = nccl_load();
+  if (st) return st;
+  nccl_uid u;
+  int r = g_nccl.GetUniqueId(&u);
+  if (r) { set_error("ncclGetUniqueId: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); return RUB_ERR_NCCL; }
+  memcpy(id, u.internal, RUB_NCCL_UNIQUE_ID_BYTES);
+  return RUB_OK;
+}
+extern "C" rub_status rub_comm_init(rub_rx *h, const uint8_t id[RUB_NCCL_UNIQUE_ID_BYTES], int rank, int world) {
+  if (!h || !id || world < 1 || rank < 0 || rank >= world) return RUB_ERR_INVALID_ARG;
+  rub_status st = nccl_load();
+  if (st) return st;
+  CUDA_TRY(cudaSetDevice(h->device));
+  nccl_uid u;
+  memcpy(u.internal, id, RUB_NCCL_UNIQUE_ID_BYTES);
+  int r = g_nccl.CommInitRank(&h->comm, world, u, rank);
+  if (r) { set_error("ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); h->comm = nullptr; return RUB_ERR_NCCL; }
+  h->rank = rank;
+  h->world = world;
+  return RUB_OK;
+}
+// one ncclAllReduce(sum, uint64) over the 4*N error counters, on the handle's stream
+extern "C" rub_status rub_allreduce_counters(rub_rx *h) {
+  if (!h) return RUB_ERR_INVALID_ARG;
+  if (!h->comm) { if (h->world == 1) return RUB_OK; set_error("rub_comm_init not called"); return RUB_ERR_NCCL; }
+  CUDA_TRY(cudaSetDevice(h->device));
+  int r = g_nccl.AllReduce(h->d_counters, h->d_counters, 4 * h->h.N, /*ncclUint64*/ 5, /*ncclSum*/ 0, h->comm, h->stream);
+  if (r) { set_error("ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); return RUB_ERR_NCCL; }
+  h->launches += 1;
+  return RUB_OK;
+}
+extern "C" rub_status rub_comm_destroy(rub_rx *h) {
+  if (!h) return RUB_ERR_INVALID_ARG;
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  h->comm = nullptr;
+  return RUB_OK;
+}
