@@ -395,6 +395,7 @@ class Receiver:
         self.h = C.c_void_p()
         stream = None
         dev = -1
+        self.tstream = None
         if device_count() > 0:
             import torch
             if device is None:
@@ -402,7 +403,10 @@ class Receiver:
             dev = int(device)
             torch.cuda.set_device(dev)
             if use_torch_stream:
-                stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+                # a dedicated torch stream: torch.cuda.Event can time it and torch ops can be
+                # ordered against it (process_batch waits for torch's current stream first)
+                self.tstream = torch.cuda.Stream(device=dev)
+                stream = C.c_void_p(self.tstream.cuda_stream)
         self.device = dev
         S1 = None if S1 is None else np.ascontiguousarray(S1, np.complex64)
         _check(lib().rub_rx_create(C.byref(self.h), C.byref(cfg.c), _p(S1), dev, stream))
@@ -483,6 +487,9 @@ class Receiver:
         io.counters = None
         io.out_mask = out_mask
         self._keep = (iq, tx_data, timing, payload_start, out)
+        if self.tstream is not None:
+            import torch
+            self.tstream.wait_stream(torch.cuda.current_stream())
         _check(lib().rub_rx_process_batch(self.h, C.byref(io), n_frames))
         return out
 

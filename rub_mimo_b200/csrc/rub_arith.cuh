@@ -148,6 +148,19 @@ RUB_HD uint32_t slice_axis(float v, float alpha) {
   }
   return s;
 }
+// Same decisions, branch-free: refs[k] = 2^(m-1-k)*alpha precomputed by the caller.  v - ref and
+// v + (-ref) are the same IEEE operation, so the residual chain is bit-identical.
+template <int MBITS>
+RUB_HD uint32_t slice_axis_refs(float v, const float *refs) {
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < MBITS; k++) {
+    const bool p = v > 0.f;
+    s |= p ? (1u << (MBITS - 1 - k)) : 0u;
+    if (k + 1 < MBITS) v = v + (p ? -refs[k] : refs[k]);
+  }
+  return s;
+}
 RUB_HD uint32_t slice_axis_rt(float v, int m, float alpha) {
   uint32_t s = 0;
   for (int k = 0; k < m; k++) {

@@ -61,19 +61,30 @@ struct FftStage {
   static constexpr int B = P / R;   // butterflies per thread
   static_assert(B >= 1 && B * R == P, "plan");
 
+  // Padded index of element idx0 + t*STRIDE: when STRIDE is a multiple of 16, or the whole
+  // butterfly lives inside one 16-element pad group (NS == 1), the pad term does not depend
+  // on t and the per-element address is base + t*const (an immediate offset in SASS).
+  template <bool PAD, int STRIDE>
+  RUB_HD static int elem(int base_padded, int idx0, int t) {
+    if (!PAD) return idx0 + t * STRIDE;
+    if (STRIDE % 16 == 0) return base_padded + t * (STRIDE + STRIDE / 16);
+    if (STRIDE == 1 && R <= 16) return base_padded + t;
+    return pad_idx(idx0 + t * STRIDE);
+  }
+
   template <bool PAD_IN>
   RUB_HD static void load(int tid, const cf *in, cf *v) {
 #pragma unroll
     for (int b = 0; b < B; b++) {
       const int j = tid + b * NT;
+      const int bp = PAD_IN ? pad_idx(j) : j;
 #pragma unroll
-      for (int t = 0; t < R; t++) {
-        const int idx = j + t * Q;
-        v[b * R + t] = in[PAD_IN ? pad_idx(idx) : idx];
-      }
+      for (int t = 0; t < R; t++) v[b * R + t] = in[elem<PAD_IN, Q>(bp, j, t)];
     }
   }
-  // twiddle (skipped for the first stage, NS == 1) + butterfly
+  // twiddle (skipped for the first stage, NS == 1) + butterfly.  TW_DIRECT: tws is dereferenced
+  // directly (a shared-memory copy of the table) instead of through the read-only global path
+  template <bool TW_DIRECT = false>
   RUB_HD static void compute(int tid, cf *v, const cf *tws) {
 #pragma unroll
     for (int b = 0; b < B; b++) {
@@ -81,7 +92,8 @@ struct FftStage {
       if (NS > 1) {
         const int k = j % NS;
 #pragma unroll
-        for (int t = 1; t < R; t++) v[b * R + t] = cmul(v[b * R + t], ld_tw(tws + (t - 1) * NS + k));
+        for (int t = 1; t < R; t++)
+          v[b * R + t] = cmul(v[b * R + t], TW_DIRECT ? tws[(t - 1) * NS + k] : ld_tw(tws + (t - 1) * NS + k));
       }
       bfly<R>(v + b * R);
     }
@@ -93,12 +105,12 @@ struct FftStage {
       const int j = tid + b * NT;
       const int k = j % NS;
       const int base = (j / NS) * NS * R + k;
+      const int bp = PAD_OUT ? pad_idx(base) : base;
 #pragma unroll
       for (int t = 0; t < R; t++) {
-        const int idx = base + t * NS;
         cf val = v[b * R + t];
         if (SCALE) val = cscale(val, scale);
-        out[PAD_OUT ? pad_idx(idx) : idx] = val;
+        out[elem<PAD_OUT, NS>(bp, base, t)] = val;
       }
     }
   }

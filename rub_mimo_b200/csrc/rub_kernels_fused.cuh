@@ -11,7 +11,10 @@
 //     and completed through an mbarrier, so HBM reads overlap the previous symbol's math;
 //   * FFT: in place in the landing buffer, 3 register-radix stages, padded exchange layout;
 //   * W/gain/isig: per-CTA scratch in global memory, rewritten per frame and re-read for each
-//     of the D payload symbols (L2 resident);
+//     of the D payload symbols; kept L2 resident with an evict_last policy while every
+//     streaming access (samples in, LLR/bits/eq out, tx_data) carries evict_first;
+//   * detection is software pipelined: the W/gain/isig/tx_data registers of task i+1 are
+//     loaded while task i is computed;
 //   * LLRs and packed bits: staged per warp in shared memory in their final byte order and
 //     written with cp.async.bulk shared->global; equalised symbols go out as 16-byte
 //     coalesced stores.
@@ -41,6 +44,9 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned parity) {
   unsigned ok;
   asm volatile(
@@ -58,17 +64,30 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// L2 eviction policies: streams are read/written once (evict_first), the per-CTA W scratch
+// is re-read D times per frame (evict_last)
+__device__ __forceinline__ unsigned long long policy_evict_first() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ unsigned long long policy_evict_last() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
 __device__ __forceinline__ void bulk_load(void *dst_smem, const void *src_gmem, unsigned bytes,
-                                          unsigned long long *bar) {
+                                          unsigned long long *bar, unsigned long long pol) {
   asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
           smem_u32(dst_smem)),
-      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
       : "memory");
 }
-__device__ __forceinline__ void bulk_store(void *dst_gmem, const void *src_smem, unsigned bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
-               "r"(smem_u32(src_smem)), "r"(bytes)
+__device__ __forceinline__ void bulk_store(void *dst_gmem, const void *src_smem, unsigned bytes,
+                                           unsigned long long pol) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst_gmem),
+               "r"(smem_u32(src_smem)), "r"(bytes), "l"(pol)
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -83,23 +102,37 @@ __device__ __forceinline__ void group_sync(int id) {
   if (NTHR % 32 == 0) asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NTHR) : "memory");
   else __syncthreads();
 }
-__device__ __forceinline__ float4 ldcg4(const void *p) { return __ldcg(reinterpret_cast<const float4 *>(p)); }
-__device__ __forceinline__ float2 ldcg2(const void *p) { return __ldcg(reinterpret_cast<const float2 *>(p)); }
-
-// demap of one equalised symbol: returns the symbol index, writes 2*MB LLRs
-template <int MB>
-__device__ __forceinline__ unsigned demap_one(cf z, float isig, float alpha, const float *lut_slope,
-                                              const float *lut_icpt, float *llr, bool want_llr) {
-  constexpr int PL = 1 << MB;
-  const unsigned si = slice_axis<MB>(z.x, alpha), sq = slice_axis<MB>(z.y, alpha);
-  if (want_llr) {
-#pragma unroll
-    for (int b = 0; b < MB; b++) {
-      llr[b] = fmaf(lut_slope[b * PL + si], z.x, lut_icpt[b * PL + si]) * isig;
-      llr[MB + b] = fmaf(lut_slope[b * PL + sq], z.y, lut_icpt[b * PL + sq]) * isig;
-    }
-  }
-  return (gray_encode(si) << MB) + gray_encode(sq);
+__device__ __forceinline__ float4 ld_hint4(const void *p, unsigned long long pol) {
+  float4 v;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float2 ld_hint2(const void *p, unsigned long long pol) {
+  float2 v;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;"
+               : "=f"(v.x), "=f"(v.y)
+               : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ unsigned ld_hint_u16(const void *p, unsigned long long pol) {
+  unsigned short v;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st_hint4(void *p, float4 v, unsigned long long pol) {
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x),
+               "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void st_hint2(void *p, float2 v, unsigned long long pol) {
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y),
+               "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void st_hint1(void *p, float v, unsigned long long pol) {
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
 }
 
 template <int LOG2M, int N>
@@ -107,74 +140,154 @@ struct FusedTraits {
   using FF = Fft<LOG2M>;
   static constexpr int M = FF::M, NT = FF::NT, THREADS = N * NT, PAD = fft_padded_size(M);
   static constexpr int NWARPS = THREADS / 32;
-  static constexpr int TASKS = N * M / 64;  // (stream, 64-carrier block) per OFDM symbol
+  static constexpr int TASKS = N * M / 64;        // (stream, 64-carrier block) per OFDM symbol
+  static constexpr int TPW = TASKS / NWARPS;      // tasks per warp per symbol (= M / (2 NT))
+  static constexpr int KSTEP = 2 * NT;            // carrier distance between a warp's tasks
   static constexpr int BUF_ELEMS = N * PAD;
-  static_assert(THREADS % 32 == 0, "fused path needs whole warps");
+  // NT is a multiple of 32, so NWARPS = N*NT/32 is a multiple of N: a warp always serves the
+  // same stream s = warp % N and carrier blocks kb0 + it*NT/32
+  static_assert(NT % 32 == 0, "fused path needs NT to be whole warps");
+  static_assert(TPW * NWARPS == TASKS && (TPW % 2) == 0, "task split");
   static size_t smem_bytes(int q) {
-    return (size_t)2 * BUF_ELEMS * sizeof(cf) + (size_t)NWARPS * 2 * (256 * q + 64) + 2 * 64 * sizeof(float) +
-           64 /* mbarriers + counters */ + 8 * N * 2;
+    return (size_t)2 * BUF_ELEMS * sizeof(cf) + (size_t)NWARPS * 2 * (256 * q + 64) + 64 * sizeof(float2) +
+           (size_t)FftTw<LOG2M>::TOTAL * sizeof(cf) + 64 /* mbarriers */ + 8 * N * 2 + 64;
   }
 };
 
-// one detection task: stream s, carriers [k0, k0+64); lane owns carriers k0+2*lane, +1
+// registers of one detection task: stream s, carriers [k0, k0+64); lane owns k0+2*lane, +1
+template <int N>
+struct TaskRegs {
+  float4 w[N];   // W[s][r][k], W[s][r][k+1]
+  float2 g, is;  // gain, 1/sigma_eff^2 of the two carriers
+  unsigned tx;   // two transmitted symbol indices (when counting errors)
+};
+
+// per-warp constants of the detection phase (fixed for the whole kernel)
+struct WarpCtx {
+  const cf *Wp;        // W scratch at (s, r=0, first carrier of this lane)
+  const float *gp, *ip;
+  float *lp[2];        // this lane's slice of the two LLR staging slots
+  unsigned char *bp[2];  // this lane group's bytes of the two packed-bit staging slots
+  unsigned char *slot[2];
+  int koff;            // first carrier of this lane: kb0*64 + 2*lane
+  int s;
+};
+
+template <int N, int M>
+__device__ __forceinline__ void task_load(TaskRegs<N> &t, const WarpCtx &c, int kadd, const unsigned char *txp,
+                                          unsigned long long pol_keep, unsigned long long pol_stream) {
+#pragma unroll
+  for (int r = 0; r < N; r++) t.w[r] = ld_hint4(c.Wp + r * M + kadd, pol_keep);
+  t.g = ld_hint2(c.gp + kadd, pol_keep);
+  t.is = ld_hint2(c.ip + kadd, pol_keep);
+  t.tx = txp ? ld_hint_u16(txp + kadd, pol_stream) : 0u;
+}
+
+// demap of one equalised symbol: returns the symbol index, writes 2*MB LLRs
+template <int MB>
+__device__ __forceinline__ unsigned demap_one(cf z, float isig, const float *refs, const float2 *lut, float *llr,
+                                              bool want_llr) {
+  constexpr int PL = 1 << MB;
+  const unsigned si = slice_axis_refs<MB>(z.x, refs), sq = slice_axis_refs<MB>(z.y, refs);
+  if (want_llr) {
+    const float2 *li = lut + si, *lq = lut + sq;
+#pragma unroll
+    for (int b = 0; b < MB; b++) {
+      const float2 ci = li[b * PL], cq = lq[b * PL];
+      llr[b] = fmaf(ci.x, z.x, ci.y) * isig;
+      llr[MB + b] = fmaf(cq.x, z.y, cq.y) * isig;
+    }
+  }
+  // (gray(si) << MB) | gray(sq) in one pass: the shifted-in bit that crosses from si into sq's
+  // top position is masked off
+  const unsigned c = (si << MB) | sq;
+  return c ^ ((c >> 1) & ~(1u << (MB - 1)));
+}
+
 template <int N, int MB>
-__device__ __forceinline__ void detect_task(const FusedArgs &fa, const cf *Y, int PAD, const cf *Wc,
-                                            const float *gc, const float *ic, int M, int s, int k0,
-                                            long long orow, float *llr_stage, unsigned char *bit_stage,
-                                            const float *lut_slope, const float *lut_icpt, float alpha,
-                                            unsigned &be, unsigned &se) {
+__device__ __forceinline__ void task_compute(const TaskRegs<N> &t, const ChainArgs &a, const cf *Yk, int PAD,
+                                             long long o, float *lp, unsigned char *bp, const float2 *lut,
+                                             const float *refs, unsigned long long pol_stream, unsigned &be,
+                                             unsigned &se) {
   constexpr int Q = 2 * MB;
-  const ChainArgs &a = fa.a;
   const int lane = threadIdx.x & 31;
-  const int k = k0 + 2 * lane;
   cf acc0 = mk(0.f, 0.f), acc1 = mk(0.f, 0.f);
 #pragma unroll
   for (int r = 0; r < N; r++) {
-    const float4 w = ldcg4(Wc + ((long long)(s * N + r)) * M + k);
-    const float4 y = *reinterpret_cast<const float4 *>(Y + (long long)r * PAD + k);
-    acc0 = cmac(acc0, mk(w.x, w.y), mk(y.x, y.y));
-    acc1 = cmac(acc1, mk(w.z, w.w), mk(y.z, y.w));
+    const float4 y = *reinterpret_cast<const float4 *>(Yk + r * PAD);
+    acc0 = cmac(acc0, mk(t.w[r].x, t.w[r].y), mk(y.x, y.y));
+    acc1 = cmac(acc1, mk(t.w[r].z, t.w[r].w), mk(y.z, y.w));
   }
-  const float2 g = ldcg2(gc + (long long)s * M + k);
-  const float2 is = ldcg2(ic + (long long)s * M + k);
-  const cf z0 = cscale(acc0, g.x), z1 = cscale(acc1, g.y);
+  const cf z0 = cscale(acc0, t.g.x), z1 = cscale(acc1, t.g.y);
   float l0[Q], l1[Q];
   const bool want_llr = a.llr != nullptr;
-  const unsigned sym0 = demap_one<MB>(z0, is.x, alpha, lut_slope, lut_icpt, l0, want_llr);
-  const unsigned sym1 = demap_one<MB>(z1, is.y, alpha, lut_slope, lut_icpt, l1, want_llr);
-  const long long o = orow * M + k;
-  if (a.eq) *reinterpret_cast<float4 *>(a.eq + o) = make_float4(z0.x, z0.y, z1.x, z1.y);
-  if (a.rx_data) *reinterpret_cast<uchar2 *>(a.rx_data + o) = make_uchar2((unsigned char)sym0, (unsigned char)sym1);
+  const unsigned sym0 = demap_one<MB>(z0, t.is.x, refs, lut, l0, want_llr);
+  const unsigned sym1 = demap_one<MB>(z1, t.is.y, refs, lut, l1, want_llr);
+  const unsigned rx2 = sym0 | (sym1 << 8);
+  if (a.eq) st_hint4(a.eq + o, make_float4(z0.x, z0.y, z1.x, z1.y), pol_stream);
+  if (a.rx_data) *reinterpret_cast<unsigned short *>(a.rx_data + o) = (unsigned short)rx2;
   if (want_llr) {
-    float *lp = llr_stage + lane * 2 * Q;  // [k][bit] order, 2*Q floats per lane
-    if (Q == 2) {
-      *reinterpret_cast<float4 *>(lp) = make_float4(l0[0], l0[1], l1[0], l1[1]);
-    } else {
-      float tmp[2 * Q];
+    float tmp[2 * Q];  // [k][bit] order, 2*Q floats per lane
 #pragma unroll
-      for (int b = 0; b < Q; b++) { tmp[b] = l0[b]; tmp[Q + b] = l1[b]; }
+    for (int b = 0; b < Q; b++) { tmp[b] = l0[b]; tmp[Q + b] = l1[b]; }
 #pragma unroll
-      for (int v = 0; v < 2 * Q / 4; v++)
-        *reinterpret_cast<float4 *>(lp + 4 * v) = make_float4(tmp[4 * v], tmp[4 * v + 1], tmp[4 * v + 2], tmp[4 * v + 3]);
-    }
+    for (int v = 0; v < 2 * Q / 4; v++)
+      *reinterpret_cast<float4 *>(lp + 4 * v) = make_float4(tmp[4 * v], tmp[4 * v + 1], tmp[4 * v + 2], tmp[4 * v + 3]);
   }
   if (a.bits) {
     // 4 lanes = 8 symbols = Q bytes, MSB first
-    unsigned v2 = (sym0 << Q) | sym1;                       // 2Q bits
+    const unsigned v2 = (sym0 << Q) | sym1;                                   // 2Q bits
     const unsigned p1 = __shfl_xor_sync(0xffffffffu, v2, 1);
-    unsigned long long v4 = ((unsigned long long)v2 << (2 * Q)) | p1;  // valid on even lanes, 4Q bits
-    const unsigned long long p2 = __shfl_xor_sync(0xffffffffu, v4, 2);
+    const unsigned v4 = (v2 << (2 * Q)) | p1;                                 // even lanes: 4Q bits
+    const unsigned p2 = __shfl_xor_sync(0xffffffffu, v4, 2);
     if ((lane & 3) == 0) {
-      const unsigned long long v8 = (v4 << (4 * Q)) | p2;   // 8Q bits = Q bytes
-      unsigned char *bp = bit_stage + (lane >> 2) * Q;
+      const unsigned long long v8 = ((unsigned long long)v4 << (4 * Q)) | p2;  // 8Q bits = Q bytes
+      // big-endian byte order, written as Q/2 byte-swapped halfwords (bp is 2-byte aligned)
 #pragma unroll
-      for (int i = 0; i < Q; i++) bp[i] = (unsigned char)(v8 >> (8 * (Q - 1 - i)));
+      for (int i = 0; i < Q / 2; i++) {
+        const unsigned hw = (unsigned)(v8 >> (16 * (Q / 2 - 1 - i))) & 0xffffu;
+        reinterpret_cast<unsigned short *>(bp)[i] = (unsigned short)__byte_perm(hw, 0, 0x4401);
+      }
     }
   }
   if (a.tx_data) {
-    const uchar2 t = *reinterpret_cast<const uchar2 *>(a.tx_data + o);
-    be += __popc((unsigned)t.x ^ sym0) + __popc((unsigned)t.y ^ sym1);
-    se += ((unsigned)t.x != sym0) + ((unsigned)t.y != sym1);
+    const unsigned x = rx2 ^ t.tx;
+    be += __popc(x);
+    se += ((x & 0xffu) != 0u) + ((x >> 8) != 0u);
+  }
+}
+
+// detection of one payload OFDM symbol by the whole CTA; `cur` already holds task 0
+template <int LOG2M, int N, int MB>
+__device__ __forceinline__ void detect_symbol(const FusedArgs &fa, TaskRegs<N> &cur, const WarpCtx &wc,
+                                              const cf *buf, long long symbase, const float2 *lut,
+                                              const float *refs, unsigned long long pol_keep,
+                                              unsigned long long pol_stream, unsigned &acc_be, unsigned &acc_se) {
+  using TR = FusedTraits<LOG2M, N>;
+  constexpr int M = TR::M, PAD = TR::PAD, TPW = TR::TPW, KSTEP = TR::KSTEP, Q = 2 * MB;
+  const ChainArgs &a = fa.a;
+  const int lane = threadIdx.x & 31;
+  const long long obase = symbase + (long long)wc.s * (a.D * M) + wc.koff;  // this lane, task 0
+  const unsigned char *txp = a.tx_data ? a.tx_data + obase : nullptr;
+  const cf *Yl = buf + wc.koff;
+  TaskRegs<N> nxt;
+#pragma unroll
+  for (int it = 0; it < TPW; it++) {
+    if (it + 1 < TPW) task_load<N, M>(nxt, wc, (it + 1) * KSTEP, txp, pol_keep, pol_stream);
+    // the bulk store issued two tasks ago from this staging slot must have drained
+    if (lane == 0) bulk_wait_read<1>();
+    __syncwarp();
+    task_compute<N, MB>(cur, a, Yl + it * KSTEP, PAD, obase + it * KSTEP, wc.lp[it & 1], wc.bp[it & 1], lut, refs,
+                        pol_stream, acc_be, acc_se);
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      const long long ob = obase - 2 * lane + it * KSTEP;  // first symbol of the 64-carrier block
+      if (a.llr) bulk_store(a.llr + ob * Q, wc.slot[it & 1], (unsigned)(64 * Q * 4), pol_stream);
+      if (a.bits) bulk_store(a.bits + (ob >> 3) * Q, wc.slot[it & 1] + fa.llr_stage_bytes, (unsigned)(8 * Q), pol_stream);
+      bulk_commit();
+    }
+    if (it + 1 < TPW) cur = nxt;
   }
 }
 
@@ -191,95 +304,145 @@ __global__ void __launch_bounds__(FusedTraits<LOG2M, N>::THREADS) k_rx_fused(Fus
   cf *buf1 = buf0 + TR::BUF_ELEMS;
   unsigned char *stage_base = reinterpret_cast<unsigned char *>(buf1 + TR::BUF_ELEMS);
   const int stage_stride = fa.llr_stage_bytes + 64;  // llr block followed by 64 B of packed bits
-  float *lut_slope = reinterpret_cast<float *>(stage_base + (size_t)NWARPS * 2 * stage_stride);
-  float *lut_icpt = lut_slope + 64;
-  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(lut_icpt + 64);
-  unsigned *cnt = reinterpret_cast<unsigned *>(mbar + 2);  // [N][2] bit errors, symbol errors
+  float2 *lut = reinterpret_cast<float2 *>(stage_base + (size_t)NWARPS * 2 * stage_stride);
+  cf *tw_s = reinterpret_cast<cf *>(lut + 64);  // stage twiddles, copied once
+  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(tw_s + TW::TOTAL);  // full[2], empty[2]
+  unsigned *cnt = reinterpret_cast<unsigned *>(mbar + 4);  // [N][2] bit errors, symbol errors
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ant = tid / NT, ft = tid % NT;
   const int nsym = a.T + a.D;
   const int q = a.q;
+  const unsigned long long pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
 
-  if (tid < 64) { lut_slope[tid] = lutp.slope[tid]; lut_icpt[tid] = lutp.icpt[tid]; }
+  if (tid < 64) lut[tid] = make_float2(lutp.slope[tid], lutp.icpt[tid]);
+  for (int i = tid; i < TW::TOTAL; i += THREADS) tw_s[i] = a.tw[i];
   if (tid < 2 * N) cnt[tid] = 0;
   if (tid == 0) {
     mbar_init(&mbar[0], 1);
     mbar_init(&mbar[1], 1);
+    mbar_init(&mbar[2], NWARPS);
+    mbar_init(&mbar[3], NWARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
   }
   __syncthreads();
 
   const int nf_cta = (a.n_frames - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const long long total = (long long)nf_cta * nsym;  // flat (frame, symbol) sequence of this CTA
+  const int total = nf_cta * nsym;  // flat (frame, symbol) sequence of this CTA
   cf *Wc = fa.scratchW + (size_t)blockIdx.x * N * N * M;
   float *gc = fa.scratchG + (size_t)blockIdx.x * 2 * N * M, *ic = gc + (size_t)N * M;
   const unsigned sym_bytes = (unsigned)(M * sizeof(cf));
 
-  auto issue_load = [&](long long g) {  // thread 0 only
-    const int fl = (int)(g / nsym), sym = (int)(g % nsym);
+  // detection constants of this warp / lane
+  WarpCtx wc;
+  wc.s = warp % N;
+  wc.koff = (warp / N) * 64 + 2 * lane;
+  wc.Wp = Wc + (size_t)wc.s * N * M + wc.koff;
+  wc.gp = gc + (size_t)wc.s * M + wc.koff;
+  wc.ip = ic + (size_t)wc.s * M + wc.koff;
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    wc.slot[i] = stage_base + (size_t)(warp * 2 + i) * stage_stride;
+    wc.lp[i] = reinterpret_cast<float *>(wc.slot[i]) + lane * 2 * q;
+    wc.bp[i] = wc.slot[i] + fa.llr_stage_bytes + (lane >> 2) * q;
+  }
+  float refs[4];  // liquid ref[k] = 2^k * alpha, most significant first
+#pragma unroll
+  for (int i = 0; i < 4; i++) refs[i] = (i < q / 2) ? (float)(1u << (q / 2 - 1 - i)) * lutp.alpha : 0.f;
+
+  auto issue_load = [&](int g) {  // thread 0 only
+    const int fl = g / nsym, sym = g - fl * nsym;
     const long long frame = (long long)blockIdx.x + (long long)fl * gridDim.x;
     cf *dst = (g & 1) ? buf1 : buf0;
     unsigned long long *bar = &mbar[g & 1];
     mbar_expect_tx(bar, sym_bytes * N);
     const cf *src = a.iq + frame * a.frame_stride + a.first_sample + (long long)sym * a.L + a.cp;
 #pragma unroll
-    for (int r = 0; r < N; r++) bulk_load(dst + (size_t)r * PAD, src + (long long)r * a.rx_stride, sym_bytes, bar);
+    for (int r = 0; r < N; r++)
+      bulk_load(dst + (size_t)r * PAD, src + (long long)r * a.rx_stride, sym_bytes, bar, pol_stream);
   };
   if (tid == 0) {
     if (total > 0) issue_load(0);
     if (total > 1) issue_load(1);
   }
 
-  for (long long g = 0; g < total; g++) {
-    const int fl = (int)(g / nsym), sym = (int)(g % nsym);
+  unsigned acc_be = 0, acc_se = 0;
+  int fl = 0, sym = 0;
+  for (int g = 0; g < total; g++) {
     const long long frame = (long long)blockIdx.x + (long long)fl * gridDim.x;
     cf *buf = (g & 1) ? buf1 : buf0;
     cf *mine = buf + (size_t)ant * PAD;
+    const bool payload = sym >= a.T;
+    const long long symbase = (frame * N * a.D + (sym - a.T)) * (long long)M;
+    TaskRegs<N> cur;
+    auto prefetch_task0 = [&]() {
+      // W/gain/isig/tx_data of this warp's first detection task, issued before the last FFT
+      // stage so the L2 latency hides behind it
+      if (payload) {
+        const long long obase = symbase + (long long)wc.s * (a.D * M) + wc.koff;
+        task_load<N, M>(cur, wc, 0, a.tx_data ? a.tx_data + obase : nullptr, pol_keep, pol_stream);
+      }
+    };
+    // every warp releases `buf` (its last generic-proxy access is done) so that thread 0 may
+    // refill it by TMA one iteration later
+    auto release_buf = [&]() {
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&mbar[2 + (g & 1)]);
+    };
     mbar_wait(&mbar[g & 1], (unsigned)((g >> 1) & 1));
 
     // ---------------- FFT of the N antennas, in place ----------------
     {
       cf v[FF::PTS];
+      const float scale = payload ? a.dn : 1.0f;
       FF::S0::template load<false>(ft, mine, v);
       group_sync<NT>(1 + ant);
       FF::S0::compute(ft, v, nullptr);
       FF::S0::template store<true, false>(ft, v, mine, 1.f);
       group_sync<NT>(1 + ant);
+      if (tid == 0 && g >= 1 && g + 1 < total) {
+        // the other buffer held symbol g-1: refill it once every warp has released it
+        mbar_wait(&mbar[2 + ((g + 1) & 1)], (unsigned)(((g - 1) >> 1) & 1));
+        issue_load(g + 1);
+      }
+      if (PL::NSTG == 2) prefetch_task0();
       FF::S1::template load<true>(ft, mine, v);
       group_sync<NT>(1 + ant);
-      FF::S1::compute(ft, v, a.tw + TW::OFF1);
-      const float scale = sym >= a.T ? a.dn : 1.0f;
+      FF::S1::template compute<true>(ft, v, tw_s + TW::OFF1);
       if (PL::NSTG == 2) {
         FF::S1::template store<false, true>(ft, v, mine, scale);
       } else {
         FF::S1::template store<true, false>(ft, v, mine, 1.f);
         group_sync<NT>(1 + ant);
+        prefetch_task0();
         FF::S2::template load<true>(ft, mine, v);
         group_sync<NT>(1 + ant);
-        FF::S2::compute(ft, v, a.tw + TW::OFF2);
+        FF::S2::template compute<true>(ft, v, tw_s + TW::OFF2);
         FF::S2::template store<false, true>(ft, v, mine, scale);
       }
     }
     __syncthreads();
 
-    if (sym < a.T) {
+    if (!payload) {
       // ---------------- LS accumulate (mimo/framing.cc:801-815) ----------------
       const int c = sym / N, t = sym % N;
       const bool q1 = (a.flags & RUB_FLAG_Q1_IDENTITY_INIT) != 0;
+#pragma unroll
       for (int e = tid; e < N * M / 2; e += THREADS) {
         const int r = e / (M / 2), k = 2 * (e % (M / 2));
         const float4 x = *reinterpret_cast<const float4 *>(buf + (size_t)r * PAD + k);
         const float2 sg = __ldg(reinterpret_cast<const float2 *>(a.sgn + ((size_t)t * a.nac + c) * M + k));
-        float4 *gp = reinterpret_cast<float4 *>(Wc + (size_t)(r * N + t) * M + k);
+        cf *gp = Wc + (size_t)(r * N + t) * M + k;
         float4 acc;
         if (c == 0) { const float d = (q1 && r == t) ? 1.0f : 0.0f; acc = make_float4(d, 0.f, d, 0.f); }
-        else acc = __ldcg(gp);
+        else acc = ld_hint4(gp, pol_keep);
         acc.x = acc.x + x.x * sg.x; acc.y = acc.y + x.y * sg.x;
         acc.z = acc.z + x.z * sg.y; acc.w = acc.w + x.w * sg.y;
-        __stcg(gp, acc);
+        st_hint4(gp, acc, pol_keep);
       }
+      release_buf();
       if (sym == a.T - 1) {
         // ---------------- weights (mimo/framing.cc:817-832) ----------------
         __syncthreads();
@@ -288,7 +451,7 @@ __global__ void __launch_bounds__(FusedTraits<LOG2M, N>::THREADS) k_rx_fused(Fus
           float gain[N], isig[N];
 #pragma unroll
           for (int e = 0; e < N * N; e++) {
-            const float2 t2 = ldcg2(Wc + (size_t)e * M + k);
+            const float2 t2 = ld_hint2(Wc + (size_t)e * M + k, pol_keep);
             G[e] = cscale(mk(t2.x, t2.y), a.s_ls);
           }
           if (a.G) {
@@ -297,50 +460,32 @@ __global__ void __launch_bounds__(FusedTraits<LOG2M, N>::THREADS) k_rx_fused(Fus
           }
           compute_weights<N>(fa.wm, G, W, gain, isig);
 #pragma unroll
-          for (int e = 0; e < N * N; e++) __stcg(reinterpret_cast<float2 *>(Wc + (size_t)e * M + k), make_float2(W[e].x, W[e].y));
+          for (int e = 0; e < N * N; e++) st_hint2(Wc + (size_t)e * M + k, make_float2(W[e].x, W[e].y), pol_keep);
 #pragma unroll
-          for (int s = 0; s < N; s++) { __stcg(gc + (size_t)s * M + k, gain[s]); __stcg(ic + (size_t)s * M + k, isig[s]); }
+          for (int s = 0; s < N; s++) { st_hint1(gc + (size_t)s * M + k, gain[s], pol_keep); st_hint1(ic + (size_t)s * M + k, isig[s], pol_keep); }
         }
       }
     } else {
       // ---------------- detect + demap + count ----------------
-      const int d = sym - a.T;
-      for (int tsk = warp; tsk < TR::TASKS; tsk += NWARPS) {
-        const int s = tsk % N, k0 = (tsk / N) * 64;
-        const int it = (tsk / NWARPS) & 1;
-        unsigned char *stg = stage_base + (size_t)(warp * 2 + it) * stage_stride;
-        float *llr_stage = reinterpret_cast<float *>(stg);
-        unsigned char *bit_stage = stg + fa.llr_stage_bytes;
-        // the bulk store issued two tasks ago from this staging slot must have drained
-        if (lane == 0) bulk_wait_read<1>();
-        __syncwarp();
-        const long long orow = (frame * N + s) * a.D + d;
-        unsigned tbe = 0, tse = 0;
-        switch (q) {
-          case 2: detect_task<N, 1>(fa, buf, PAD, Wc, gc, ic, M, s, k0, orow, llr_stage, bit_stage, lut_slope, lut_icpt, lutp.alpha, tbe, tse); break;
-          case 4: detect_task<N, 2>(fa, buf, PAD, Wc, gc, ic, M, s, k0, orow, llr_stage, bit_stage, lut_slope, lut_icpt, lutp.alpha, tbe, tse); break;
-          case 6: detect_task<N, 3>(fa, buf, PAD, Wc, gc, ic, M, s, k0, orow, llr_stage, bit_stage, lut_slope, lut_icpt, lutp.alpha, tbe, tse); break;
-          default: detect_task<N, 4>(fa, buf, PAD, Wc, gc, ic, M, s, k0, orow, llr_stage, bit_stage, lut_slope, lut_icpt, lutp.alpha, tbe, tse); break;
-        }
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          if (a.llr) bulk_store(a.llr + (orow * M + k0) * q, llr_stage, (unsigned)(64 * q * 4));
-          if (a.bits) bulk_store(a.bits + orow * a.row_bytes + (long long)k0 * q / 8, bit_stage, (unsigned)(8 * q));
-          bulk_commit();
-        }
-        if (a.tx_data) {
-          for (int off = 16; off; off >>= 1) {
-            tbe += __shfl_xor_sync(0xffffffffu, tbe, off);
-            tse += __shfl_xor_sync(0xffffffffu, tse, off);
-          }
-          if (lane == 0) { atomicAdd(&cnt[2 * s], tbe); atomicAdd(&cnt[2 * s + 1], tse); }
-        }
+      switch (q) {
+        case 2: detect_symbol<LOG2M, N, 1>(fa, cur, wc, buf, symbase, lut, refs, pol_keep, pol_stream, acc_be, acc_se); break;
+        case 4: detect_symbol<LOG2M, N, 2>(fa, cur, wc, buf, symbase, lut, refs, pol_keep, pol_stream, acc_be, acc_se); break;
+        case 6: detect_symbol<LOG2M, N, 3>(fa, cur, wc, buf, symbase, lut, refs, pol_keep, pol_stream, acc_be, acc_se); break;
+        default: detect_symbol<LOG2M, N, 4>(fa, cur, wc, buf, symbase, lut, refs, pol_keep, pol_stream, acc_be, acc_se); break;
       }
+      release_buf();
     }
-    __syncthreads();  // every read of `buf` is done: it may be refilled
-    if (tid == 0 && g + 2 < total) { fence_async_smem(); issue_load(g + 2); }
-    if (sym == nsym - 1 && a.tx_data && a.counters && tid < N) {
+    const bool frame_end = sym == nsym - 1;
+    if (frame_end && a.tx_data) {
+      for (int off = 16; off; off >>= 1) {
+        acc_be += __shfl_xor_sync(0xffffffffu, acc_be, off);
+        acc_se += __shfl_xor_sync(0xffffffffu, acc_se, off);
+      }
+      if (lane == 0) { atomicAdd(&cnt[2 * wc.s], acc_be); atomicAdd(&cnt[2 * wc.s + 1], acc_se); }
+      acc_be = 0; acc_se = 0;
+    }
+    if (frame_end && a.tx_data) __syncthreads();  // shared counters complete
+    if (frame_end && a.tx_data && a.counters && tid < N) {
       atomicAdd(&a.counters[tid * 4 + 0], (unsigned long long)cnt[2 * tid]);
       atomicAdd(&a.counters[tid * 4 + 1], (unsigned long long)a.D * M * q);
       atomicAdd(&a.counters[tid * 4 + 2], (unsigned long long)cnt[2 * tid + 1]);
@@ -348,6 +493,7 @@ __global__ void __launch_bounds__(FusedTraits<LOG2M, N>::THREADS) k_rx_fused(Fus
       cnt[2 * tid] = 0;
       cnt[2 * tid + 1] = 0;
     }
+    if (++sym == nsym) { sym = 0; fl++; }
   }
   if (lane == 0) bulk_wait_all();
 }
