@@ -1,0 +1,117 @@
+"""BASELINE.json's full-size configurations on the GPU, checked through size-independent
+properties (the oracle would take minutes on them): path agreement, sharding invariance,
+spot frames against the oracle, bits/LLR/rx_data consistency, counter bookkeeping."""
+import numpy as np
+import pytest
+
+import rub_mimo_b200 as rub
+from util import oracle_run
+
+pytestmark = pytest.mark.gpu
+
+
+def run(cfg, S1, d_iq, d_tx, path, mask):
+    rx = rub.Receiver(cfg, S1)
+    rx.set_path(path)
+    out = rx.process_batch(d_iq, out_mask=mask, tx_data=d_tx)
+    rx.sync()
+    c = rx.read_counters()
+    p = rx.last_path
+    rx.close()
+    return out, c, p
+
+
+@pytest.mark.parametrize("name,frames,unique", [("C2", 4096, 64), ("C3", 1024, 32)])
+def test_full_size_properties(name, frames, unique):
+    import torch
+    cfg = rub.preset(name)
+    syn = dict(rub.PRESET_SYNTH[name]); seed = syn.pop("seed")
+    S1, s1 = rub.default_S1(cfg)
+    iq_u, tx_u, nv = rub.synth_frames(cfg, unique, seed, S1=S1, s1=s1, **syn)
+    cfg = cfg.with_noise_var(nv)
+    reps = frames // unique
+    d_iq = torch.from_numpy(iq_u).cuda().repeat(reps, 1, 1)
+    d_tx = torch.from_numpy(tx_u).cuda().repeat(reps, 1, 1, 1)
+    mask = rub.OUT_EQ | rub.OUT_LLR | rub.OUT_BITS | rub.OUT_RXDATA
+    fused, cf, pf = run(cfg, S1, d_iq, d_tx, rub.PATH_AUTO, mask)
+    assert pf == rub.PATH_FUSED
+    # (1) counters: every symbol counted once, identical tiles give identical error counts
+    assert np.all(cf[:, 3] == frames * cfg.D * cfg.Mo) and np.all(cf[:, 1] == cf[:, 3] * cfg.q)
+    # (2) tiling invariance: every repetition of the unique block decodes identically
+    for k in ("eq", "llr", "bits", "rx_data"):
+        v = fused[k].reshape(reps, unique, *fused[k].shape[1:])
+        assert bool((v == v[0:1]).all()), k
+    # (3) the staged path agrees bit for bit on the unique block, and its counters scale
+    staged, cs, ps = run(cfg, S1, d_iq[:unique].contiguous(), d_tx[:unique].contiguous(), rub.PATH_STAGED, mask)
+    assert ps == rub.PATH_STAGED
+    for k in ("eq", "llr", "bits", "rx_data"):
+        assert torch.equal(staged[k], fused[k][:unique]), k
+    assert np.array_equal(cs * reps, cf)
+    # (4) spot frames against the CPU oracle
+    pick = [0, unique // 2, unique - 1]
+    ref = oracle_run(cfg, S1, iq_u[pick], tx_u[pick])
+    for i, f in enumerate(pick):
+        assert np.array_equal(ref["rx_data"][i], fused["rx_data"][f].cpu().numpy())
+        assert np.array_equal(ref["bits"][i], fused["bits"][f].cpu().numpy())
+        assert np.array_equal(ref["eq"][i], fused["eq"][f].cpu().numpy())
+        assert np.array_equal(ref["llr"][i], fused["llr"][f].cpu().numpy())
+    # (5) internal consistency at full size: packed bits == rx_data bits; LLR sign vs hard bit
+    rxd = fused["rx_data"][:unique].cpu().numpy()
+    q = cfg.q
+    b = ((rxd[..., None] >> (q - 1 - np.arange(q))) & 1).astype(np.uint8).reshape(*rxd.shape[:3], -1)
+    assert np.array_equal(np.packbits(b, axis=-1), fused["bits"][:unique].cpu().numpy())
+    llr = fused["llr"][:unique].cpu().numpy().reshape(*rxd.shape[:3], -1)
+    assert np.all((llr < 0) <= (b == 1)) and np.all((llr > 0) <= (b == 0))
+    # (6) symbol errors recomputed from rx_data equal the counters
+    se = (fused["rx_data"] != d_tx).sum(dim=(0, 2, 3)).cpu().numpy()
+    assert np.array_equal(se, cf[:, 2].astype(np.int64))
+
+
+def test_sharding_is_invariant():
+    """C5 property: counters of 2 shards add up to the single-batch counters (frames independent)."""
+    import torch
+    cfg = rub.preset("C3")
+    syn = dict(rub.PRESET_SYNTH["C3"]); seed = syn.pop("seed")
+    S1, s1 = rub.default_S1(cfg)
+    iq, tx, nv = rub.synth_frames(cfg, 10, seed, S1=S1, s1=s1, **syn)
+    cfg = cfg.with_noise_var(nv)
+    d_iq, d_tx = torch.from_numpy(iq).cuda(), torch.from_numpy(tx).cuda()
+    whole, cw, _ = run(cfg, S1, d_iq, d_tx, rub.PATH_AUTO, rub.OUT_RXDATA)
+    parts = []
+    for r in range(2):
+        b, e = rub.shard_range(10, r, 2)
+        # the shard regenerates its own frames from the global frame index
+        iq_s, tx_s, _ = rub.synth_frames(cfg, e - b, seed, first_frame=b, S1=S1, s1=s1, **syn)
+        out, c, _ = run(cfg, S1, torch.from_numpy(iq_s).cuda(), torch.from_numpy(tx_s).cuda(), rub.PATH_AUTO, rub.OUT_RXDATA)
+        assert torch.equal(out["rx_data"], whole["rx_data"][b:e])
+        parts.append(c)
+    assert np.array_equal(parts[0] + parts[1], cw)
+
+
+def test_output_mask_subsets_and_missing_pointer():
+    import torch
+    cfg = rub.preset("C2", num_data_symbols=3)
+    S1, s1 = rub.default_S1(cfg)
+    iq, tx, nv = rub.synth_frames(cfg, 4, 3, n_taps=1, snr_db=20.0, S1=S1, s1=s1)
+    cfg = cfg.with_noise_var(nv)
+    d_iq = torch.from_numpy(iq).cuda()
+    full, _, _ = run(cfg, S1, d_iq, None, rub.PATH_AUTO, rub.OUT_EQ | rub.OUT_LLR | rub.OUT_BITS | rub.OUT_RXDATA)
+    for path in (rub.PATH_FUSED, rub.PATH_STAGED):
+        for mask in (rub.OUT_BITS, rub.OUT_LLR, rub.OUT_EQ | rub.OUT_RXDATA):
+            out, c, _ = run(cfg, S1, d_iq, None, path, mask)
+            for k in out:
+                assert torch.equal(out[k], full[k])
+            assert c.sum() == 0                      # no tx_data: counters untouched
+    rx = rub.Receiver(cfg, S1)
+    io_out = rx.alloc_outputs(4, rub.OUT_EQ)
+    with pytest.raises(rub.RubError):
+        rx.process_batch(d_iq, out=io_out, out_mask=rub.OUT_EQ | rub.OUT_LLR)
+    rx.set_path(rub.PATH_FUSED)
+    odd = torch.from_numpy(np.ascontiguousarray(np.pad(iq, ((0, 0), (0, 0), (1, 0))))).cuda()
+    with pytest.raises(rub.RubError):                # odd first_sample: cp.async.bulk alignment
+        rx.process_batch(odd, out=io_out, out_mask=rub.OUT_EQ, first_sample=1)
+    rx.set_path(rub.PATH_AUTO)
+    out = rx.process_batch(odd, out_mask=rub.OUT_EQ, first_sample=1)
+    rx.sync()
+    assert rx.last_path == rub.PATH_STAGED and torch.equal(out["eq"], full["eq"])
+    rx.close()

@@ -12,8 +12,11 @@ def to_orc(cfg):
                       sctype=cfg.sctype)
 
 
-def make_case(cfg, n_frames, seed, n_taps=4, snr_db=30.0, fixed_H=None, n_threads=0):
+def make_case(cfg, n_frames, seed, n_taps=4, snr_db=30.0, fixed_H=None, n_threads=0, fixed_H_ri=None):
     """Returns (cfg with noise_var filled in, S1, iq, tx_data)."""
+    if fixed_H_ri is not None:  # JSON form: [re, im] pairs
+        a = np.asarray(fixed_H_ri, np.float32)
+        fixed_H = a[..., 0] + 1j * a[..., 1]
     S1, s1 = rub.default_S1(cfg)
     iq, tx, nv = rub.synth_frames(cfg, n_frames, seed, n_taps=n_taps, snr_db=snr_db,
                                   fixed_H=fixed_H, S1=S1, s1=s1, n_threads=n_threads)
