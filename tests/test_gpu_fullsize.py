@@ -61,7 +61,12 @@ def test_full_size_properties(name, frames, unique):
     b = ((rxd[..., None] >> (q - 1 - np.arange(q))) & 1).astype(np.uint8).reshape(*rxd.shape[:3], -1)
     assert np.array_equal(np.packbits(b, axis=-1), fused["bits"][:unique].cpu().numpy())
     llr = fused["llr"][:unique].cpu().numpy().reshape(*rxd.shape[:3], -1)
-    assert np.all((llr < 0) <= (b == 1)) and np.all((llr > 0) <= (b == 0))
+    # sign(LLR) agrees with the hard bit except within fp32 rounding of a decision threshold,
+    # where the LLR magnitude is ~1e-7 of the symbol's LLR scale (DESIGN.md "Demapper")
+    bad = ((llr < 0) & (b == 0)) | ((llr > 0) & (b == 1))
+    assert bad.mean() < 1e-5
+    lmax = np.abs(llr.reshape(*rxd.shape, q)).max(axis=-1).repeat(q, axis=-1).reshape(llr.shape)
+    assert np.all(np.abs(llr[bad]) <= 1e-4 * lmax[bad])
     # (6) symbol errors recomputed from rx_data equal the counters
     se = (fused["rx_data"] != d_tx).sum(dim=(0, 2, 3)).cpu().numpy()
     assert np.array_equal(se, cf[:, 2].astype(np.int64))
