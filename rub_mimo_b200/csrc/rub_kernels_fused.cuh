@@ -142,15 +142,15 @@ struct FusedTraits {
   static constexpr int NWARPS = THREADS / 32;
   static constexpr int TASKS = N * M / 64;        // (stream, 64-carrier block) per OFDM symbol
   static constexpr int TPW = TASKS / NWARPS;      // tasks per warp per symbol (= M / (2 NT))
-  static constexpr int KSTEP = 2 * NT;            // carrier distance between a warp's tasks
+  static constexpr int KPW = TPW / N;             // 64-carrier blocks per warp: all N streams of a
+                                                  // block are served by one warp (Y is read once)
+  static constexpr int KSTEP = 64 * NWARPS;       // carrier distance between a warp's blocks
   static constexpr int BUF_ELEMS = N * PAD;
-  // NT is a multiple of 32, so NWARPS = N*NT/32 is a multiple of N: a warp always serves the
-  // same stream s = warp % N and carrier blocks kb0 + it*NT/32
   static_assert(NT % 32 == 0, "fused path needs NT to be whole warps");
-  static_assert(TPW * NWARPS == TASKS && (TPW % 2) == 0, "task split");
+  static_assert(KPW >= 1 && KPW * N * NWARPS == TASKS && (TPW % 2) == 0, "task split");
   static size_t smem_bytes(int q) {
     return (size_t)2 * BUF_ELEMS * sizeof(cf) + (size_t)NWARPS * 2 * (256 * q + 64) + 64 * sizeof(float2) +
-           (size_t)FftTw<LOG2M>::TOTAL * sizeof(cf) + 64 /* mbarriers */ + 8 * N * 2 + 64;
+           (size_t)FftTw<LOG2M>::TOTAL * sizeof(cf) + (size_t)2 * N * M /* tx_data */ + 64 /* mbarriers */ + 8 * N * 2 + 64;
   }
 };
 
@@ -159,28 +159,24 @@ template <int N>
 struct TaskRegs {
   float4 w[N];   // W[s][r][k], W[s][r][k+1]
   float2 g, is;  // gain, 1/sigma_eff^2 of the two carriers
-  unsigned tx;   // two transmitted symbol indices (when counting errors)
 };
 
 // per-warp constants of the detection phase (fixed for the whole kernel)
 struct WarpCtx {
-  const cf *Wp;        // W scratch at (s, r=0, first carrier of this lane)
-  const float *gp, *ip;
-  float *lp[2];        // this lane's slice of the two LLR staging slots
-  unsigned char *bp[2];  // this lane group's bytes of the two packed-bit staging slots
-  unsigned char *slot[2];
-  int koff;            // first carrier of this lane: kb0*64 + 2*lane
-  int s;
+  const cf *Wp;          // W scratch at (s=0, r=0, first carrier of this lane)
+  const float *gp;       // gain scratch at (s=0, first carrier); isig follows N*M floats later
+  unsigned char *slot0;  // this warp's first staging slot (the second follows stage_stride bytes later)
+  int stage_stride;
+  int koff;              // first carrier of this lane: warp*64 + 2*lane
 };
 
 template <int N, int M>
-__device__ __forceinline__ void task_load(TaskRegs<N> &t, const WarpCtx &c, int kadd, const unsigned char *txp,
-                                          unsigned long long pol_keep, unsigned long long pol_stream) {
+__device__ __forceinline__ void task_load(TaskRegs<N> &t, const WarpCtx &c, int s, int kadd,
+                                          unsigned long long pol_keep) {
 #pragma unroll
-  for (int r = 0; r < N; r++) t.w[r] = ld_hint4(c.Wp + r * M + kadd, pol_keep);
-  t.g = ld_hint2(c.gp + kadd, pol_keep);
-  t.is = ld_hint2(c.ip + kadd, pol_keep);
-  t.tx = txp ? ld_hint_u16(txp + kadd, pol_stream) : 0u;
+  for (int r = 0; r < N; r++) t.w[r] = ld_hint4(c.Wp + (s * N + r) * M + kadd, pol_keep);
+  t.g = ld_hint2(c.gp + s * M + kadd, pol_keep);
+  t.is = ld_hint2(c.gp + (N + s) * M + kadd, pol_keep);
 }
 
 // demap of one equalised symbol: returns the symbol index, writes 2*MB LLRs
@@ -205,16 +201,16 @@ __device__ __forceinline__ unsigned demap_one(cf z, float isig, const float *ref
 }
 
 template <int N, int MB>
-__device__ __forceinline__ void task_compute(const TaskRegs<N> &t, const ChainArgs &a, const cf *Yk, int PAD,
+__device__ __forceinline__ void task_compute(const TaskRegs<N> &t, const ChainArgs &a, const float4 *y4,
                                              long long o, float *lp, unsigned char *bp, const float2 *lut,
-                                             const float *refs, unsigned long long pol_stream, unsigned &be,
-                                             unsigned &se) {
+                                             const float *refs, unsigned long long pol_stream,
+                                             const unsigned char *txs, unsigned *cnt_s) {
   constexpr int Q = 2 * MB;
   const int lane = threadIdx.x & 31;
   cf acc0 = mk(0.f, 0.f), acc1 = mk(0.f, 0.f);
 #pragma unroll
   for (int r = 0; r < N; r++) {
-    const float4 y = *reinterpret_cast<const float4 *>(Yk + r * PAD);
+    const float4 y = y4[r];
     acc0 = cmac(acc0, mk(t.w[r].x, t.w[r].y), mk(y.x, y.y));
     acc1 = cmac(acc1, mk(t.w[r].z, t.w[r].w), mk(y.z, y.w));
   }
@@ -251,43 +247,62 @@ __device__ __forceinline__ void task_compute(const TaskRegs<N> &t, const ChainAr
     }
   }
   if (a.tx_data) {
-    const unsigned x = rx2 ^ t.tx;
-    be += __popc(x);
-    se += ((x & 0xffu) != 0u) + ((x >> 8) != 0u);
+    // warp-uniform address: ptxas turns each atomicAdd into REDUX.SUM + one ATOMS per warp
+    const unsigned x = rx2 ^ (unsigned)*reinterpret_cast<const unsigned short *>(txs);
+    atomicAdd(cnt_s, (unsigned)__popc(x));
+    atomicAdd(cnt_s + 1, (unsigned)((x & 0xffu) != 0u) + (unsigned)((x >> 8) != 0u));
   }
 }
 
-// detection of one payload OFDM symbol by the whole CTA; `cur` already holds task 0
+// detection of one payload OFDM symbol by the whole CTA; `cur` already holds task 0.
+// A warp walks KPW blocks of 64 carriers; for each block it reads Y once (N x 16 B per lane) and
+// serves the N streams one after the other.
 template <int LOG2M, int N, int MB>
 __device__ __forceinline__ void detect_symbol(const FusedArgs &fa, TaskRegs<N> &cur, const WarpCtx &wc,
-                                              const cf *buf, long long symbase, const float2 *lut,
+                                              const cf *buf, const unsigned char *txs, long long symbase,
+                                              const float2 *lut,
                                               const float *refs, unsigned long long pol_keep,
-                                              unsigned long long pol_stream, unsigned &acc_be, unsigned &acc_se) {
+                                              unsigned long long pol_stream, unsigned *cnt) {
   using TR = FusedTraits<LOG2M, N>;
-  constexpr int M = TR::M, PAD = TR::PAD, TPW = TR::TPW, KSTEP = TR::KSTEP, Q = 2 * MB;
+  constexpr int M = TR::M, PAD = TR::PAD, KPW = TR::KPW, KSTEP = TR::KSTEP, Q = 2 * MB;
   const ChainArgs &a = fa.a;
   const int lane = threadIdx.x & 31;
-  const long long obase = symbase + (long long)wc.s * (a.D * M) + wc.koff;  // this lane, task 0
-  const unsigned char *txp = a.tx_data ? a.tx_data + obase : nullptr;
+  const int DM = a.D * M;
+  const long long obase = symbase + wc.koff;  // stream 0, block 0, this lane
   const cf *Yl = buf + wc.koff;
+  const unsigned char *txl = txs + wc.koff;   // transmitted symbols of this OFDM symbol, [stream][k] in smem
   TaskRegs<N> nxt;
 #pragma unroll
-  for (int it = 0; it < TPW; it++) {
-    if (it + 1 < TPW) task_load<N, M>(nxt, wc, (it + 1) * KSTEP, txp, pol_keep, pol_stream);
-    // the bulk store issued two tasks ago from this staging slot must have drained
-    if (lane == 0) bulk_wait_read<1>();
-    __syncwarp();
-    task_compute<N, MB>(cur, a, Yl + it * KSTEP, PAD, obase + it * KSTEP, wc.lp[it & 1], wc.bp[it & 1], lut, refs,
-                        pol_stream, acc_be, acc_se);
-    fence_async_smem();
-    __syncwarp();
-    if (lane == 0) {
-      const long long ob = obase - 2 * lane + it * KSTEP;  // first symbol of the 64-carrier block
-      if (a.llr) bulk_store(a.llr + ob * Q, wc.slot[it & 1], (unsigned)(64 * Q * 4), pol_stream);
-      if (a.bits) bulk_store(a.bits + (ob >> 3) * Q, wc.slot[it & 1] + fa.llr_stage_bytes, (unsigned)(8 * Q), pol_stream);
-      bulk_commit();
+  for (int kb = 0; kb < KPW; kb++) {
+    float4 y4[N];
+#pragma unroll
+    for (int r = 0; r < N; r++) y4[r] = *reinterpret_cast<const float4 *>(Yl + r * PAD + kb * KSTEP);
+#pragma unroll
+    for (int s = 0; s < N; s++) {
+      constexpr int dummy = 0; (void)dummy;
+      const int it = kb * N + s;
+      if (it + 1 < KPW * N) {
+        const int sn = (s + 1) % N, kn = (s + 1 == N) ? kb + 1 : kb;
+        task_load<N, M>(nxt, wc, sn, kn * KSTEP, pol_keep);
+      }
+      // the bulk store issued two tasks ago from this staging slot must have drained
+      if (lane == 0) bulk_wait_read<1>();
+      __syncwarp();
+      const long long o = obase + (long long)s * DM + kb * KSTEP;
+      unsigned char *slot = wc.slot0 + (it & 1) * wc.stage_stride;
+      task_compute<N, MB>(cur, a, y4, o, reinterpret_cast<float *>(slot) + lane * 2 * Q,
+                          slot + fa.llr_stage_bytes + (lane >> 2) * Q, lut, refs, pol_stream, txl + s * M + kb * KSTEP,
+                          cnt + 2 * s);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        const long long ob = o - 2 * lane;  // first symbol of the 64-carrier block
+        if (a.llr) bulk_store(a.llr + ob * Q, slot, (unsigned)(64 * Q * 4), pol_stream);
+        if (a.bits) bulk_store(a.bits + (ob >> 3) * Q, slot + fa.llr_stage_bytes, (unsigned)(8 * Q), pol_stream);
+        bulk_commit();
+      }
+      if (it + 1 < KPW * N) cur = nxt;
     }
-    if (it + 1 < TPW) cur = nxt;
   }
 }
 
@@ -306,7 +321,8 @@ __global__ void __launch_bounds__(FusedTraits<LOG2M, N>::THREADS) k_rx_fused(Fus
   const int stage_stride = fa.llr_stage_bytes + 64;  // llr block followed by 64 B of packed bits
   float2 *lut = reinterpret_cast<float2 *>(stage_base + (size_t)NWARPS * 2 * stage_stride);
   cf *tw_s = reinterpret_cast<cf *>(lut + 64);  // stage twiddles, copied once
-  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(tw_s + TW::TOTAL);  // full[2], empty[2]
+  unsigned char *txbuf = reinterpret_cast<unsigned char *>(tw_s + TW::TOTAL);  // [2][N][M] tx symbols
+  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(txbuf + 2 * N * M);  // full[2], empty[2]
   unsigned *cnt = reinterpret_cast<unsigned *>(mbar + 4);  // [N][2] bit errors, symbol errors
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -336,17 +352,11 @@ __global__ void __launch_bounds__(FusedTraits<LOG2M, N>::THREADS) k_rx_fused(Fus
 
   // detection constants of this warp / lane
   WarpCtx wc;
-  wc.s = warp % N;
-  wc.koff = (warp / N) * 64 + 2 * lane;
-  wc.Wp = Wc + (size_t)wc.s * N * M + wc.koff;
-  wc.gp = gc + (size_t)wc.s * M + wc.koff;
-  wc.ip = ic + (size_t)wc.s * M + wc.koff;
-#pragma unroll
-  for (int i = 0; i < 2; i++) {
-    wc.slot[i] = stage_base + (size_t)(warp * 2 + i) * stage_stride;
-    wc.lp[i] = reinterpret_cast<float *>(wc.slot[i]) + lane * 2 * q;
-    wc.bp[i] = wc.slot[i] + fa.llr_stage_bytes + (lane >> 2) * q;
-  }
+  wc.koff = warp * 64 + 2 * lane;
+  wc.Wp = Wc + wc.koff;
+  wc.gp = gc + wc.koff;
+  wc.slot0 = stage_base + (size_t)(warp * 2) * stage_stride;
+  wc.stage_stride = stage_stride;
   float refs[4];  // liquid ref[k] = 2^k * alpha, most significant first
 #pragma unroll
   for (int i = 0; i < 4; i++) refs[i] = (i < q / 2) ? (float)(1u << (q / 2 - 1 - i)) * lutp.alpha : 0.f;
@@ -356,18 +366,25 @@ __global__ void __launch_bounds__(FusedTraits<LOG2M, N>::THREADS) k_rx_fused(Fus
     const long long frame = (long long)blockIdx.x + (long long)fl * gridDim.x;
     cf *dst = (g & 1) ? buf1 : buf0;
     unsigned long long *bar = &mbar[g & 1];
-    mbar_expect_tx(bar, sym_bytes * N);
+    const bool with_tx = a.tx_data && sym >= a.T;
+    mbar_expect_tx(bar, sym_bytes * N + (with_tx ? N * M : 0));
     const cf *src = a.iq + frame * a.frame_stride + a.first_sample + (long long)sym * a.L + a.cp;
 #pragma unroll
     for (int r = 0; r < N; r++)
       bulk_load(dst + (size_t)r * PAD, src + (long long)r * a.rx_stride, sym_bytes, bar, pol_stream);
+    if (with_tx) {
+      // the transmitted symbol indices of this OFDM symbol ride on the same mbarrier
+      const unsigned char *tsrc = a.tx_data + (frame * N * a.D + (sym - a.T)) * (long long)M;
+#pragma unroll
+      for (int s = 0; s < N; s++)
+        bulk_load(txbuf + ((g & 1) * N + s) * M, tsrc + (long long)s * a.D * M, M, bar, pol_stream);
+    }
   };
   if (tid == 0) {
     if (total > 0) issue_load(0);
     if (total > 1) issue_load(1);
   }
 
-  unsigned acc_be = 0, acc_se = 0;
   int fl = 0, sym = 0;
   for (int g = 0; g < total; g++) {
     const long long frame = (long long)blockIdx.x + (long long)fl * gridDim.x;
@@ -380,8 +397,7 @@ __global__ void __launch_bounds__(FusedTraits<LOG2M, N>::THREADS) k_rx_fused(Fus
       // W/gain/isig/tx_data of this warp's first detection task, issued before the last FFT
       // stage so the L2 latency hides behind it
       if (payload) {
-        const long long obase = symbase + (long long)wc.s * (a.D * M) + wc.koff;
-        task_load<N, M>(cur, wc, 0, a.tx_data ? a.tx_data + obase : nullptr, pol_keep, pol_stream);
+        task_load<N, M>(cur, wc, 0, 0, pol_keep);
       }
     };
     // every warp releases `buf` (its last generic-proxy access is done) so that thread 0 may
@@ -468,22 +484,14 @@ __global__ void __launch_bounds__(FusedTraits<LOG2M, N>::THREADS) k_rx_fused(Fus
     } else {
       // ---------------- detect + demap + count ----------------
       switch (q) {
-        case 2: detect_symbol<LOG2M, N, 1>(fa, cur, wc, buf, symbase, lut, refs, pol_keep, pol_stream, acc_be, acc_se); break;
-        case 4: detect_symbol<LOG2M, N, 2>(fa, cur, wc, buf, symbase, lut, refs, pol_keep, pol_stream, acc_be, acc_se); break;
-        case 6: detect_symbol<LOG2M, N, 3>(fa, cur, wc, buf, symbase, lut, refs, pol_keep, pol_stream, acc_be, acc_se); break;
-        default: detect_symbol<LOG2M, N, 4>(fa, cur, wc, buf, symbase, lut, refs, pol_keep, pol_stream, acc_be, acc_se); break;
+        case 2: detect_symbol<LOG2M, N, 1>(fa, cur, wc, buf, txbuf + (g & 1) * N * M, symbase, lut, refs, pol_keep, pol_stream, cnt); break;
+        case 4: detect_symbol<LOG2M, N, 2>(fa, cur, wc, buf, txbuf + (g & 1) * N * M, symbase, lut, refs, pol_keep, pol_stream, cnt); break;
+        case 6: detect_symbol<LOG2M, N, 3>(fa, cur, wc, buf, txbuf + (g & 1) * N * M, symbase, lut, refs, pol_keep, pol_stream, cnt); break;
+        default: detect_symbol<LOG2M, N, 4>(fa, cur, wc, buf, txbuf + (g & 1) * N * M, symbase, lut, refs, pol_keep, pol_stream, cnt); break;
       }
       release_buf();
     }
     const bool frame_end = sym == nsym - 1;
-    if (frame_end && a.tx_data) {
-      for (int off = 16; off; off >>= 1) {
-        acc_be += __shfl_xor_sync(0xffffffffu, acc_be, off);
-        acc_se += __shfl_xor_sync(0xffffffffu, acc_se, off);
-      }
-      if (lane == 0) { atomicAdd(&cnt[2 * wc.s], acc_be); atomicAdd(&cnt[2 * wc.s + 1], acc_se); }
-      acc_be = 0; acc_se = 0;
-    }
     if (frame_end && a.tx_data) __syncthreads();  // shared counters complete
     if (frame_end && a.tx_data && a.counters && tid < N) {
       atomicAdd(&a.counters[tid * 4 + 0], (unsigned long long)cnt[2 * tid]);

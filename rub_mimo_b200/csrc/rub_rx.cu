@@ -143,7 +143,7 @@ static bool fused_eligible(const rub_rx *h, const rub_rx_io *io, uint64_t frame_
   // cp.async.bulk needs 16-byte aligned sources: even sample offsets everywhere
   if ((c.cp | c.L | io->layout.first_sample | frame_stride | rx_stride) & 1) return false;
   if (((uintptr_t)io->iq & 15) || ((uintptr_t)io->llr & 15) || ((uintptr_t)io->bits & 15) || ((uintptr_t)io->eq & 15)) return false;
-  if (((uintptr_t)io->rx_data & 1) || ((uintptr_t)io->tx_data & 1)) return false;
+  if (((uintptr_t)io->rx_data & 1) || ((uintptr_t)io->tx_data & 15)) return false;
   return true;
 }
 
