@@ -27,6 +27,7 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     "C3": dict(preset="C3", frames_per_gpu=1024, unique=64, label="C3 4x4/2048sc/cp152/64-QAM/MMSE+LLR nac2 D14"),
     "C2": dict(preset="C2", frames_per_gpu=4096, unique=128, label="C2 2x2/1024sc/cp72/16-QAM/ZF nac2 D14"),
+    "C4": dict(preset="C4", frames_per_gpu=256, unique=16, label="C4 8x8/4096sc/cp288/256-QAM/MMSE comb-interp nac2 D14"),
 }
 
 
@@ -178,7 +179,9 @@ def run_ours(args):
     # are tiled to fill it (input 1.6 GB + output 3.9 GB per step: far beyond the 126 MB L2)
     d_iq = torch.from_numpy(iq_u).cuda().repeat(reps, 1, 1)[:F].contiguous()
     d_tx = torch.from_numpy(tx_u).cuda().repeat(reps, 1, 1, 1)[:F].contiguous()
-    out_mask = rub.OUT_EQ | rub.OUT_LLR | rub.OUT_BITS
+    out_mask = 0
+    for name in args.outputs.split("+"):
+        out_mask |= {"eq": rub.OUT_EQ, "llr": rub.OUT_LLR, "bits": rub.OUT_BITS, "rx_data": rub.OUT_RXDATA}[name]
     rx = rub.Receiver(cfg, S1, device=local)
     if args.path:
         rx.set_path({"staged": rub.PATH_STAGED, "fused": rub.PATH_FUSED}[args.path])
@@ -291,7 +294,7 @@ def run_ours(args):
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": f"synthetic ({U} unique frames tiled to {F} per GPU)",
             "config": {"workload": wl["label"], "frames_per_gpu": F, "frames_total": F * world,
-                       "outputs": "eq+llr+bits+counters", "path": path,
+                       "outputs": args.outputs + "+counters", "path": path,
                        "l2": "inputs+outputs per step (5.5 GB) exceed the 126 MB L2; no flush needed",
                        "parallelism": f"frame-sharded x{world}, ncclAllReduce(uint64 counters) per step"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -319,6 +322,7 @@ def main():
     ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
     ap.add_argument("--frames", type=int, default=0, help="frames per GPU (default: workload's)")
     ap.add_argument("--path", default="", choices=["", "staged", "fused"])
+    ap.add_argument("--outputs", default="eq+llr+bits", help="subset of eq+llr+bits+rx_data (default: all three)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -204,7 +204,7 @@ template <int N, int MB>
 __device__ __forceinline__ void task_compute(const TaskRegs<N> &t, const ChainArgs &a, const float4 *y4,
                                              long long o, float *lp, unsigned char *bp, const float2 *lut,
                                              const float *refs, unsigned long long pol_stream,
-                                             const unsigned char *txs, unsigned *cnt_s) {
+                                             unsigned txv, unsigned *cnt_s) {
   constexpr int Q = 2 * MB;
   const int lane = threadIdx.x & 31;
   cf acc0 = mk(0.f, 0.f), acc1 = mk(0.f, 0.f);
@@ -248,7 +248,7 @@ __device__ __forceinline__ void task_compute(const TaskRegs<N> &t, const ChainAr
   }
   if (a.tx_data) {
     // warp-uniform address: ptxas turns each atomicAdd into REDUX.SUM + one ATOMS per warp
-    const unsigned x = rx2 ^ (unsigned)*reinterpret_cast<const unsigned short *>(txs);
+    const unsigned x = rx2 ^ txv;
     atomicAdd(cnt_s, (unsigned)__popc(x));
     atomicAdd(cnt_s + 1, (unsigned)((x & 0xffu) != 0u) + (unsigned)((x >> 8) != 0u));
   }
@@ -291,7 +291,8 @@ __device__ __forceinline__ void detect_symbol(const FusedArgs &fa, TaskRegs<N> &
       const long long o = obase + (long long)s * DM + kb * KSTEP;
       unsigned char *slot = wc.slot0 + (it & 1) * wc.stage_stride;
       task_compute<N, MB>(cur, a, y4, o, reinterpret_cast<float *>(slot) + lane * 2 * Q,
-                          slot + fa.llr_stage_bytes + (lane >> 2) * Q, lut, refs, pol_stream, txl + s * M + kb * KSTEP,
+                          slot + fa.llr_stage_bytes + (lane >> 2) * Q, lut, refs, pol_stream,
+                          a.tx_data ? (unsigned)*reinterpret_cast<const unsigned short *>(txl + s * M + kb * KSTEP) : 0u,
                           cnt + 2 * s);
       fence_async_smem();
       __syncwarp();
@@ -504,6 +505,85 @@ __global__ void __launch_bounds__(FusedTraits<LOG2M, N>::THREADS) k_rx_fused(Fus
     if (++sym == nsym) { sym = 0; fl++; }
   }
   if (lane == 0) bulk_wait_all();
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// k_detect_blocks: detection for the staged path when every carrier is occupied (e.g. C4, 8x8 /
+// 4096, whose 256 KB of FFT output per symbol does not fit one CTA's shared memory).  Same lane
+// mapping, per-task code and TMA bulk stores as the fused kernel, but Y, W, gain, isig and
+// tx_data come from HBM/L2 (written by k_fft_staged / k_weights).  One warp per (frame, symbol,
+// 64-carrier block); it reads Y once and serves the N streams in turn.
+template <int N, int MB>
+__global__ void __launch_bounds__(128) k_detect_blocks(ChainArgs a, DemapLut lutp, int llr_stage_bytes) {
+  constexpr int Q = 2 * MB;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ float2 lut[64];
+  __shared__ unsigned cnt[2 * N];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < 64) lut[tid] = make_float2(lutp.slope[tid], lutp.icpt[tid]);
+  if (tid < 2 * N) cnt[tid] = 0;
+  __syncthreads();
+  const int M = a.M;
+  const int blocks_per_sym = M / 64;
+  const long long wid = (long long)blockIdx.x * 4 + warp;            // (frame, symbol, block)
+  const long long nwork = (long long)a.n_frames * a.D * blocks_per_sym;
+  const unsigned long long pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
+  float refs[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) refs[i] = (i < MB) ? (float)(1u << (MB - 1 - i)) * lutp.alpha : 0.f;
+  if (wid < nwork) {
+    const int kb = (int)(wid % blocks_per_sym);
+    const int d = (int)((wid / blocks_per_sym) % a.D);
+    const long long frame = wid / ((long long)blocks_per_sym * a.D);
+    const int k = kb * 64 + 2 * lane;
+    const long long nsym = a.T + a.D;
+    const cf *Yf = a.Y + ((frame * nsym + a.T + d) * N) * M + k;
+    const cf *Wf = a.W + frame * N * N * M + k;
+    const float *gf = a.gain + frame * N * M + k, *sf = a.isig + frame * N * M + k;
+    float4 y4[N];
+#pragma unroll
+    for (int r = 0; r < N; r++) y4[r] = ld_hint4(Yf + (long long)r * M, pol_stream);
+    const int stage_stride = llr_stage_bytes + 64;
+    const long long DM = (long long)a.D * M;
+    const long long obase = (frame * N * a.D + d) * (long long)M + k;
+#pragma unroll 1
+    for (int s = 0; s < N; s++) {
+      TaskRegs<N> t;
+#pragma unroll
+      for (int r = 0; r < N; r++) t.w[r] = ld_hint4(Wf + (long long)(s * N + r) * M, pol_keep);
+      t.g = ld_hint2(gf + (long long)s * M, pol_keep);
+      t.is = ld_hint2(sf + (long long)s * M, pol_keep);
+      unsigned char *slot = smem_raw + (size_t)(warp * 2 + (s & 1)) * stage_stride;
+      if (lane == 0) bulk_wait_read<1>();
+      __syncwarp();
+      const long long o = obase + s * DM;
+      // task_compute reads the transmitted symbols through a pointer: global memory works too
+      task_compute<N, MB>(t, a, y4, o, reinterpret_cast<float *>(slot) + lane * 2 * Q,
+                          slot + llr_stage_bytes + (lane >> 2) * Q, lut, refs, pol_stream,
+                          a.tx_data ? ld_hint_u16(a.tx_data + o, pol_stream) : 0u, cnt + 2 * s);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        const long long ob = o - 2 * lane;
+        if (a.llr) bulk_store(a.llr + ob * Q, slot, (unsigned)(64 * Q * 4), pol_stream);
+        if (a.bits) bulk_store(a.bits + (ob >> 3) * Q, slot + llr_stage_bytes, (unsigned)(8 * Q), pol_stream);
+        bulk_commit();
+      }
+    }
+    if (lane == 0) bulk_wait_all();
+  }
+  __syncthreads();
+  if (a.tx_data && a.counters && tid < N) {
+    const long long w0 = (long long)blockIdx.x * 4;
+    const long long nw = nwork - w0 < 4 ? nwork - w0 : 4;  // warps of this CTA that had work
+    if (nw > 0) {
+      atomicAdd(&a.counters[tid * 4 + 0], (unsigned long long)cnt[2 * tid]);
+      atomicAdd(&a.counters[tid * 4 + 1], (unsigned long long)nw * 64 * a.q);
+      atomicAdd(&a.counters[tid * 4 + 2], (unsigned long long)cnt[2 * tid + 1]);
+      atomicAdd(&a.counters[tid * 4 + 3], (unsigned long long)nw * 64);
+    }
+  }
 }
 
 }  // namespace rub

@@ -310,11 +310,38 @@ static void launch_fft(const ChainArgs &a, cudaStream_t st, cudaError_t *err) {
   const unsigned grid = (unsigned)((total + F - 1) / F);
   k_fft_staged<LOG2M, F><<<grid, NT * F, smem, st>>>(a);
 }
+template <int N, int MB>
+static void launch_detect_blocks(const ChainArgs &a, const rub_rx *h, cudaStream_t st) {
+  const int llr_stage = 256 * 2 * MB;
+  const size_t smem = (size_t)4 * 2 * (llr_stage + 64);
+  const long long nwork = (long long)a.n_frames * a.D * (a.M / 64);
+  k_detect_blocks<N, MB><<<(unsigned)((nwork + 3) / 4), 128, smem, st>>>(a, h->lut, llr_stage);
+}
+// block-mapped detect kernel: all carriers occupied, 16-byte aligned outputs, N in {1,2,4,8}
+static bool detect_blocks_ok(const ChainArgs &a) {
+  if (a.Mo != a.M || (a.M % 64)) return false;
+  if (!(a.N == 1 || a.N == 2 || a.N == 4 || a.N == 8)) return false;
+  if (((uintptr_t)a.llr & 15) || ((uintptr_t)a.bits & 15) || ((uintptr_t)a.eq & 15)) return false;
+  if (((uintptr_t)a.rx_data & 1) || ((uintptr_t)a.tx_data & 1)) return false;
+  return true;
+}
 template <int N>
 static void launch_weights_detect(const ChainArgs &a, const rub_rx *h, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1) {
   const long long tw = (long long)a.n_frames * a.M;
   k_weights<N><<<(unsigned)((tw + 127) / 128), 128, 0, st>>>(a, h->wm);
   if (e0) cudaEventRecord(e0, st);
+  if constexpr (N == 1 || N == 2 || N == 4 || N == 8) {
+    if (detect_blocks_ok(a)) {
+      switch (a.q) {
+        case 2: launch_detect_blocks<N, 1>(a, h, st); break;
+        case 4: launch_detect_blocks<N, 2>(a, h, st); break;
+        case 6: launch_detect_blocks<N, 3>(a, h, st); break;
+        default: launch_detect_blocks<N, 4>(a, h, st); break;
+      }
+      if (e1) cudaEventRecord(e1, st);
+      return;
+    }
+  }
   const int groups = (a.Mo + 7) / 8;
   dim3 grid((unsigned)((long long)a.n_frames * a.D * N), (unsigned)((groups + 127) / 128));
   k_detect<N><<<grid, 128, 0, st>>>(a, h->lut);
