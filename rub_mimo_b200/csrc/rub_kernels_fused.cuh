@@ -446,18 +446,25 @@ __global__ void __launch_bounds__(FusedTraits<LOG2M, N>::THREADS) k_rx_fused(Fus
       // ---------------- LS accumulate (mimo/framing.cc:801-815) ----------------
       const int c = sym / N, t = sym % N;
       const bool q1 = (a.flags & RUB_FLAG_Q1_IDENTITY_INIT) != 0;
+      // all read-modify-write loads first (they are ordered asm volatile: interleaving them with
+      // the stores would serialise one L2 round trip per element), then the adds and the stores
+      constexpr int LS_IT = (N * M / 2) / THREADS;
+      float4 accv[LS_IT];
 #pragma unroll
-      for (int e = tid; e < N * M / 2; e += THREADS) {
-        const int r = e / (M / 2), k = 2 * (e % (M / 2));
+      for (int i = 0; i < LS_IT; i++) {
+        const int e = tid + i * THREADS, r = e / (M / 2), k = 2 * (e % (M / 2));
+        if (c == 0) { const float d = (q1 && r == t) ? 1.0f : 0.0f; accv[i] = make_float4(d, 0.f, d, 0.f); }
+        else accv[i] = ld_hint4(Wc + (size_t)(r * N + t) * M + k, pol_keep);
+      }
+#pragma unroll
+      for (int i = 0; i < LS_IT; i++) {
+        const int e = tid + i * THREADS, r = e / (M / 2), k = 2 * (e % (M / 2));
         const float4 x = *reinterpret_cast<const float4 *>(buf + (size_t)r * PAD + k);
         const float2 sg = __ldg(reinterpret_cast<const float2 *>(a.sgn + ((size_t)t * a.nac + c) * M + k));
-        cf *gp = Wc + (size_t)(r * N + t) * M + k;
-        float4 acc;
-        if (c == 0) { const float d = (q1 && r == t) ? 1.0f : 0.0f; acc = make_float4(d, 0.f, d, 0.f); }
-        else acc = ld_hint4(gp, pol_keep);
+        float4 acc = accv[i];
         acc.x = acc.x + x.x * sg.x; acc.y = acc.y + x.y * sg.x;
         acc.z = acc.z + x.z * sg.y; acc.w = acc.w + x.w * sg.y;
-        st_hint4(gp, acc, pol_keep);
+        st_hint4(Wc + (size_t)(r * N + t) * M + k, acc, pol_keep);
       }
       release_buf();
       if (sym == a.T - 1) {
