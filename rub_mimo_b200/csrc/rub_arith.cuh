@@ -155,9 +155,20 @@ RUB_HD uint32_t slice_axis_refs(float v, const float *refs) {
   uint32_t s = 0;
 #pragma unroll
   for (int k = 0; k < MBITS; k++) {
+#if defined(__CUDA_ARCH__)
+    // one compare, two predicated adds, one predicated or (instead of compare/select/add/select)
+    if (k + 1 < MBITS)
+      asm("{\n .reg .pred p;\n setp.gt.f32 p, %1, 0f00000000;\n @p or.b32 %0, %0, %4;\n"
+          " @p add.f32 %1, %1, %2;\n @!p add.f32 %1, %1, %3;\n}"
+          : "+r"(s), "+f"(v)
+          : "f"(-refs[k]), "f"(refs[k]), "r"(1u << (MBITS - 1 - k)));
+    else
+      asm("{\n .reg .pred p;\n setp.gt.f32 p, %1, 0f00000000;\n @p or.b32 %0, %0, 1;\n}" : "+r"(s) : "f"(v));
+#else
     const bool p = v > 0.f;
     s |= p ? (1u << (MBITS - 1 - k)) : 0u;
     if (k + 1 < MBITS) v = v + (p ? -refs[k] : refs[k]);
+#endif
   }
   return s;
 }
