@@ -452,8 +452,9 @@ static rub_status run_fused(rub_rx *h, const ChainArgs &a, uint32_t n_frames, bo
 }
 
 static rub_status process_device(rub_rx *h, const rub_rx_io *io, uint32_t n_frames, bool timed) {
-  if (!h || !io || !io->iq) { set_error("process_batch: NULL argument"); return RUB_ERR_INVALID_ARG; }
-  if (n_frames == 0) return RUB_OK;
+  if (!h || !io) { set_error("process_batch: NULL argument"); return RUB_ERR_INVALID_ARG; }
+  if (n_frames == 0) return RUB_OK;  // an empty batch is a no-op (no launch, counters untouched)
+  if (!io->iq) { set_error("process_batch: iq is NULL"); return RUB_ERR_INVALID_ARG; }
   const HostCfg &c = h->h;
   CUDA_TRY(cudaSetDevice(h->device));
   const uint64_t rx_stride = io->layout.rx_stride ? io->layout.rx_stride : (uint64_t)(c.T + c.D) * c.L + io->layout.first_sample;
