@@ -130,26 +130,33 @@ __device__ __forceinline__ cf comb_pilot(const ChainArgs &a, int frame, int r, i
   }
   return cscale(acc, a.s_ls);
 }
+// thread per (frame, rx, tx, pilot i): evaluates the two pilots that bracket the P carriers
+// [k0, k0+P), k0 = t + i*P, and writes them (plus the held band edges)
 __global__ void k_ls_comb(ChainArgs a) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)a.n_frames * a.N * a.N * a.M;
-  if (i >= total) return;
-  const int k = (int)(i % a.M);
-  const int t = (int)((i / a.M) % a.N);
-  const int r = (int)((i / ((long long)a.M * a.N)) % a.N);
-  const int frame = (int)(i / ((long long)a.M * a.N * a.N));
-  const int P = a.P, last = t + (a.M / P - 1) * P;
-  cf g;
-  if (k % P == t) g = comb_pilot(a, frame, r, t, k);
-  else if (k < t) g = comb_pilot(a, frame, r, t, t);
-  else if (k > last) g = comb_pilot(a, frame, r, t, last);
-  else {
-    const int k0 = t + ((k - t) / P) * P;
-    const cf ga = comb_pilot(a, frame, r, t, k0), gb = comb_pilot(a, frame, r, t, k0 + P);
-    const float f = (float)(k - k0) * (1.0f / (float)P);
-    g = mk(fmaf(f, gb.x - ga.x, ga.x), fmaf(f, gb.y - ga.y, ga.y));
+  const int P = a.P, np = a.M / P;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)a.n_frames * a.N * a.N * np;
+  if (idx >= total) return;
+  const int i = (int)(idx % np);
+  const int t = (int)((idx / np) % a.N);
+  const int r = (int)((idx / ((long long)np * a.N)) % a.N);
+  const int frame = (int)(idx / ((long long)np * a.N * a.N));
+  cf *g = a.G + (((long long)frame * a.N + r) * a.N + t) * a.M;
+  const int k0 = t + i * P;
+  const cf ga = comb_pilot(a, frame, r, t, k0);
+  if (i == 0)
+    for (int k = 0; k < t; k++) g[k] = ga;             // hold below the first pilot
+  g[k0] = ga;
+  if (i + 1 < np) {
+    const cf gb = comb_pilot(a, frame, r, t, k0 + P);
+    const float invP = 1.0f / (float)P;
+    for (int d = 1; d < P; d++) {
+      const float f = (float)d * invP;
+      g[k0 + d] = mk(fmaf(f, gb.x - ga.x, ga.x), fmaf(f, gb.y - ga.y, ga.y));
+    }
+  } else {
+    for (int k = k0 + 1; k < a.M; k++) g[k] = ga;      // hold above the last pilot
   }
-  a.G[i] = g;
 }
 
 // ---- K3: per-subcarrier ZF / MMSE weights (mimo/framing.cc:826-832, :1344-1367) ---------

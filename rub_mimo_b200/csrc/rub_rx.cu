@@ -399,7 +399,10 @@ static rub_status run_staged(rub_rx *h, ChainArgs a, const rub_rx_io *io, uint32
     }
     CUDA_TRY(ferr);
     const long long tg = (long long)nf * c.N * c.N * c.M;
-    if (c.c.estimator == RUB_EST_LS_COMB_INTERP) k_ls_comb<<<(unsigned)((tg + 255) / 256), 256, 0, h->stream>>>(b);
+    if (c.c.estimator == RUB_EST_LS_COMB_INTERP) {
+      const long long tp = tg / c.P;  // one thread per pilot
+      k_ls_comb<<<(unsigned)((tp + 255) / 256), 256, 0, h->stream>>>(b);
+    }
     else k_ls_fullband<<<(unsigned)((tg + 255) / 256), 256, 0, h->stream>>>(b);
     const bool last = f0 + nf >= n_frames;
     cudaEvent_t e0 = (timed && last) ? h->ev[2] : nullptr, e1 = (timed && last) ? h->ev[3] : nullptr;
