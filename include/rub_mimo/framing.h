@@ -10,11 +10,11 @@
  *
  * What runs where
  *   - framegen and the ofdmframe_* helpers: host code inside the library (rub_framegen_*).
- *   - framesync::execute: the sample-serial state machine, Schmidl & Cox plateau search
- *     (framing.cc:591-637) and the access-code timing search (framing.cc:702-744) run on the
- *     host (rows f1/f2 of SURVEY.md 8 are the next GPU rows); the timing search uses the
- *     time-domain form of the same correlation, sum_k X[k] conj(S[k]) = sqrt(M) sum_n x[n]
- *     conj(s1[n]).  Everything after it — CP strip, FFT, LS estimate, invert, W*y, gain
+ *   - framesync::execute: the sample-serial state machine stays on the host, but its two hot
+ *     loops run on the GPU: the Schmidl & Cox metric (framing.cc:626-637, rub_rx_sc_metric,
+ *     bit-exact) and the access-code timing search (framing.cc:702-744, rub_rx_timing_search,
+ *     the time-domain form of the same correlation, sum_k X[k] conj(S[k]) = sqrt(M) sum_n x[n]
+ *     conj(s1[n])).  Everything after it — CP strip, FFT, LS estimate, invert, W*y, gain
  *     (framing.cc:535-589, :801-832) — is one rub_rx_process_batch_host call on the GPU with
  *     the reference's quirks Q1 (identity-initialised G), Q2 (per-link timing index) and Q4
  *     (payload start from rx stream 1) switched on, after which mimo_callback fires once per
@@ -198,29 +198,40 @@ class framesync {
   std::vector<unsigned long int> plateau_start, plateau_end;
   std::vector<bool> in_plateau;
   std::vector<std::vector<gr_complex> > history;  // every sample pushed so far (windowcf stand-in)
-  // Schmidl & Cox running sums
-  std::vector<std::complex<double> > sc_P;
-  std::vector<double> sc_R;
-  rub_rx *rx;
+  rub_rx *rx;       // decode handle (created once the number of buffered payload symbols is known)
+  rub_rx *rx_sync;  // handle used for the synchronisation kernels
   std::vector<int32_t> corr_indices;  // [rx][ac_id]
+  std::vector<std::vector<float> > sc_metric;  // S&C metric of the samples of the current execute() call
+  size_t sc_metric_base;                       // index in the call of sc_metric[s][0]
 
-  // |P|^2 / R^2 with P = sum_{M/2} conj(x[n-M/2]) x[n], R = 0.5 sum_M |x|^2 (framing.cc:626-637);
-  // the O(M)-per-sample FIR dot products of liquid are evaluated as running sums
-  float execute_sc_sync(gr_complex x, unsigned int s) {
-    const std::vector<gr_complex> &h = history[s];
-    const size_t n = h.size() - 1;  // x already pushed
-    auto at = [&](long long i) { return i >= 0 ? std::complex<double>(h[(size_t)i]) : std::complex<double>(0, 0); };
-    const std::complex<double> xd(x);
-    sc_P[s] += std::conj(at((long long)n - M2)) * xd - std::conj(at((long long)n - 2 * (long long)M2)) * at((long long)n - M2);
-    sc_R[s] += 0.5 * (std::norm(xd) - std::norm(at((long long)n - M)));
-    const double r = sc_R[s];
-    return r > 0 ? (float)(std::norm(sc_P[s]) / (r * r)) : 0.f;
+  rub_rx *sync_handle() {
+    if (!rx_sync) {
+      rub_config c = rub_detail::make_config(M, cp_len, num_streams, num_access_codes, 1, 2, p.data());
+      rub_detail::check(rub_rx_create(&rx_sync, &c, reinterpret_cast<const float *>(S1.data()), -1, nullptr));
+    }
+    return rx_sync;
   }
-  void execute_sc_sync(const gr_complex *x) {  // framing.cc:591-624
+  // |P|^2 / R^2 (framing.cc:626-637) for samples [from, num_samples) of this call, every stream, on the
+  // GPU (bit-exact with the O(M)-per-sample FIR dot products); the history supplies the look-back
+  void compute_sc_metric(std::vector<gr_complex *> const &in_buff, size_t from, size_t num_samples) {
+    sc_metric.assign(num_streams, std::vector<float>());
+    sc_metric_base = from;
+    for (unsigned int s = 0; s < num_streams; s++) {
+      const std::vector<gr_complex> &h = history[s];
+      const size_t look = std::min(h.size(), (size_t)(M + M2));
+      std::vector<gr_complex> tmp(look + (num_samples - from));
+      std::copy(h.end() - (long)look, h.end(), tmp.begin());
+      std::copy(in_buff[s] + from, in_buff[s] + num_samples, tmp.begin() + (long)look);
+      std::vector<float> y(tmp.size());
+      rub_detail::check(rub_rx_sc_metric(sync_handle(), reinterpret_cast<const float *>(tmp.data()), tmp.size(), y.data()));
+      sc_metric[s].assign(y.begin() + (long)look, y.end());
+    }
+  }
+  void execute_sc_sync(const gr_complex *x, size_t i) {  // framing.cc:591-624
     bool proceed = true;
     for (unsigned int s = 0; s < num_streams; s++) {
       history[s].push_back(x[s]);
-      const float y = execute_sc_sync(x[s], s);
+      const float y = sc_metric[s][i - sc_metric_base];
       if (y > PLATEAU_THREASHOLD) {
         if (in_plateau[s]) plateau_end[s] = num_samples_processed;
         else { in_plateau[s] = true; plateau_start[s] = num_samples_processed; plateau_end[s] = num_samples_processed; }
@@ -250,7 +261,8 @@ class framesync {
             mimo_callback _callback)
       : M(_M), M2(_M / 2), cp_len(_cp_len), symbol_len(_M + _cp_len), num_streams(_num_streams),
         num_access_codes(_num_access_codes), p(_p, _p + _M), callback(_callback), siso_tx(0), siso_rx(0),
-        pid_max(PID_MAX), sync_index(0), num_samples_processed(0), state(STATE_SEEK_PLATEAU), rx(nullptr) {
+        pid_max(PID_MAX), sync_index(0), num_samples_processed(0), state(STATE_SEEK_PLATEAU), rx(nullptr),
+        rx_sync(nullptr), sc_metric_base(0) {
     ofdmframe_validate_sctype(p.data(), M, &M_null, &M_pilot, &M_data);
     M_occupied = M_data + M_pilot;
     S0.resize(M); s0.resize(M);
@@ -268,10 +280,9 @@ class framesync {
     normalize_gain.assign(M_occupied, 1.0f);
     plateau_start.assign(num_streams, 0); plateau_end.assign(num_streams, 0); in_plateau.assign(num_streams, false);
     history.resize(num_streams);
-    sc_P.assign(num_streams, std::complex<double>(0, 0)); sc_R.assign(num_streams, 0.0);
     set_num_data_symbols(pid_max);
   }
-  ~framesync() { rub_rx_destroy(rx); }
+  ~framesync() { rub_rx_destroy(rx); rub_rx_destroy(rx_sync); }
   framesync(const framesync &) = delete;
   framesync &operator=(const framesync &) = delete;
 
@@ -302,11 +313,14 @@ class framesync {
   // framing.cc:471-506
   framesync_states_t execute(std::vector<gr_complex *> const &in_buff, unsigned int num_samples) {
     std::vector<gr_complex> x(num_streams);
-    bool break_loop = false;
+    bool break_loop = false, have_metric = false;
     for (unsigned int i = 0; i < num_samples; i++) {
       for (unsigned int s = 0; s < num_streams; s++) x[s] = in_buff[s][i];
       switch (state) {
-        case STATE_SEEK_PLATEAU: execute_sc_sync(x.data()); break;
+        case STATE_SEEK_PLATEAU:
+          if (!have_metric) { compute_sc_metric(in_buff, i, num_samples); have_metric = true; }
+          execute_sc_sync(x.data(), i);
+          break;
         case STATE_SAVE_ACCESS_CODES: execute_save_access_codes(x.data()); break;
         case STATE_MIMO: break_loop = true; break;
         default: throw std::runtime_error("framesync: state not handled");
@@ -328,24 +342,13 @@ class framesync {
       if (h.size() >= Wlen) std::copy(h.end() - (long)Wlen, h.end(), buf[s].begin());
       else std::copy(h.begin(), h.end(), buf[s].begin() + (long)(Wlen - h.size()));
     }
-    // timing search (framing.cc:702-744): argmax over i in [0, symbol_len) of the access-code
-    // correlation at i + symbol_len*(ac_id+1), evaluated in the time domain against s1
+    // timing search (framing.cc:702-744) on the GPU: argmax over i in [0, symbol_len) of the
+    // access-code correlation at i + symbol_len*(ac_id+1)
+    std::vector<gr_complex> iq((size_t)num_streams * Wlen);
+    for (unsigned int s = 0; s < num_streams; s++) std::copy(buf[s].begin(), buf[s].end(), iq.begin() + (size_t)s * Wlen);
     corr_indices.assign((size_t)num_streams * max_ac_id, 0);
-    for (unsigned int r = 0; r < num_streams; r++)
-      for (unsigned int code = 0; code < num_access_codes; code++)
-        for (unsigned int t = 0; t < num_streams; t++) {
-          const unsigned int ac = code * num_streams + t;
-          const gr_complex *tpl = s1.data() + ((size_t)t * num_access_codes + code) * M;
-          double best = 0.0;
-          for (unsigned int i = 0; i < symbol_len; i++) {
-            const size_t sample = i + (size_t)symbol_len * (ac + 1);
-            std::complex<double> acc(0, 0);
-            const gr_complex *xp = buf[r].data() + sample;
-            for (unsigned int n = 0; n < M; n++) acc += std::complex<double>(xp[n]) * std::conj(std::complex<double>(tpl[n]));
-            const double v = std::norm(acc);
-            if (v > best) { best = v; corr_indices[(size_t)r * max_ac_id + ac] = (int32_t)sample; }
-          }
-        }
+    rub_detail::check(rub_rx_timing_search(sync_handle(), reinterpret_cast<const float *>(iq.data()), Wlen,
+                                           corr_indices.data(), nullptr));
     // LS + invert + decode on the GPU: one frame, per-link windows (Q2), payload start from rx
     // stream 1's last access code (Q4, framing.cc:857), identity-initialised G (Q1)
     const int32_t payload_start = corr_indices[(size_t)(num_streams > 1 ? 1 : 0) * max_ac_id + max_ac_id - 1] + (int32_t)M;
@@ -356,9 +359,7 @@ class framesync {
     rub_rx_destroy(rx);
     rx = nullptr;
     rub_detail::check(rub_rx_create(&rx, &c, reinterpret_cast<const float *>(S1.data()), -1, nullptr));
-    std::vector<gr_complex> iq((size_t)num_streams * Wlen), eq((size_t)num_streams * D * M_occupied),
-        Gd((size_t)num_streams * num_streams * M);
-    for (unsigned int s = 0; s < num_streams; s++) std::copy(buf[s].begin(), buf[s].end(), iq.begin() + (size_t)s * Wlen);
+    std::vector<gr_complex> eq((size_t)num_streams * D * M_occupied), Gd((size_t)num_streams * num_streams * M);
     rub_rx_io io;
     std::memset(&io, 0, sizeof(io));
     io.iq = reinterpret_cast<const float *>(iq.data());

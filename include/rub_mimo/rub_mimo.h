@@ -180,6 +180,25 @@ rub_status rub_rx_last_timing(rub_rx *h, float *total_ms, float *dominant_ms);
 uint64_t rub_rx_algorithmic_bytes(const rub_rx *h, uint32_t n_frames, uint32_t out_mask,
                                   int with_tx_data);
 
+/* ------------------------------------------------ synchronisation (rows f1 / f2) ---- */
+/* Schmidl & Cox timing metric of one rx stream, framesync::execute_sc_sync(x, stream)
+ * (mimo/framing.cc:626-637): y[n] = |P[n]|^2 / R[n]^2 with P the M/2-lag autocorrelation over
+ * M/2 samples and R = 0.5 * sum of the last M |x|^2 (samples before the first are zero).  One
+ * GPU thread per output sample evaluates both sums oldest-to-newest, which is the summation
+ * order of the oracle: the metric is bit-exact.  x and y are HOST buffers.                  */
+rub_status rub_rx_sc_metric(rub_rx *h, const float *x, uint64_t num_samples, float *y);
+/* Access-code timing search of estimate_channel (mimo/framing.cc:702-744, USE_NEW_CHANNEL_EST)
+ * over the window buffer (HOST, [N][window_len] complex64, oldest sample first): for every
+ * candidate i in [0, M+cp) and every (rx, ac_id) it correlates the M samples at
+ * i + (M+cp)*(ac_id+1) with the access code and keeps the first maximum.  The correlation is
+ * evaluated in the time domain against s1 (sum_k X[k] conj(S1[k]) = sqrt(M) sum_n x[n]
+ * conj(s1[n])), so no FFT is needed.  corr_indices [N][nac*N], s0_corr_index [N] (may be NULL;
+ * correlation with the S0 preamble at offset i, framing.cc:711-721; needs rub_rx_set_S0).    */
+rub_status rub_rx_timing_search(rub_rx *h, const float *window, uint64_t window_len,
+                                int32_t *corr_indices, int32_t *s0_corr_index);
+/* time-domain S0 preamble (M complex64) used by rub_rx_timing_search's optional S0 output  */
+rub_status rub_rx_set_S0(rub_rx *h, const float *s0);
+
 /* ----------------------------------------------------------- multi-GPU ------------- */
 /* Frames are independent (framing.cc:653-886 recomputes all state per frame), so a batch
  * is sharded by frame range with no data-path collective; the only exchange is one

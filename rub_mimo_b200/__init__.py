@@ -73,7 +73,7 @@ ABI_SYMBOLS = [
     "rub_rx_create", "rub_rx_destroy", "rub_rx_process_batch", "rub_rx_process_batch_host",
     "rub_rx_sync", "rub_rx_set_path", "rub_rx_get_path", "rub_rx_reset_counters",
     "rub_rx_device_counters", "rub_rx_read_counters", "rub_rx_launch_count", "rub_rx_last_timing",
-    "rub_rx_algorithmic_bytes", "rub_comm_get_unique_id", "rub_comm_init", "rub_allreduce_counters",
+    "rub_rx_algorithmic_bytes", "rub_rx_sc_metric", "rub_rx_timing_search", "rub_rx_set_S0", "rub_comm_get_unique_id", "rub_comm_init", "rub_allreduce_counters",
     "rub_comm_destroy", "rub_shard_range", "rub_msequence_init", "rub_msequence_reset",
     "rub_msequence_advance", "rub_msequence_generate_symbol", "rub_ofdmframe_init_default_sctype",
     "rub_ofdmframe_validate_sctype", "rub_ofdmframe_init_S0", "rub_ofdmframe_init_S1",
@@ -136,6 +136,9 @@ def lib():
         L.rub_rx_read_counters.argtypes = [C.c_void_p, C.c_void_p]
         L.rub_rx_last_timing.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.rub_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.rub_rx_sc_metric.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        L.rub_rx_timing_search.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.rub_rx_set_S0.argtypes = [C.c_void_p, C.c_void_p]
         L.rub_framegen_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.rub_framegen_destroy.argtypes = [C.c_void_p]
         L.rub_framegen_write_sync_words.argtypes = [C.c_void_p, C.c_void_p]
@@ -538,6 +541,26 @@ class Receiver:
         io.out_mask = out_mask
         _check(lib().rub_rx_process_batch_host(self.h, C.byref(io), n_frames))
         return out
+
+    # -- synchronisation rows (f1/f2) --
+    def sc_metric(self, x):
+        """Schmidl & Cox metric of one stream (framing.cc:626-637); x numpy complex64."""
+        x = np.ascontiguousarray(x, np.complex64)
+        y = np.empty(x.size, np.float32)
+        _check(lib().rub_rx_sc_metric(self.h, _p(x), x.size, _p(y)))
+        return y
+
+    def set_S0(self, s0):
+        s0 = np.ascontiguousarray(s0, np.complex64)
+        _check(lib().rub_rx_set_S0(self.h, _p(s0)))
+
+    def timing_search(self, window, want_s0=False):
+        """Access-code timing search (framing.cc:702-744); window numpy complex64 [N][Wlen]."""
+        window = np.ascontiguousarray(window, np.complex64)
+        corr = np.zeros((self.cfg.N, self.cfg.nac * self.cfg.N), np.int32)
+        s0i = np.zeros(self.cfg.N, np.int32) if want_s0 else None
+        _check(lib().rub_rx_timing_search(self.h, _p(window), window.shape[1], _p(corr), _p(s0i)))
+        return (corr, s0i) if want_s0 else corr
 
     # -- multi-GPU counters --
     def comm_init(self, unique_id, rank, world_size):

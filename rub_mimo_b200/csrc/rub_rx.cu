@@ -12,6 +12,7 @@
 #include "rub_internal.h"
 #include "rub_kernels_fused.cuh"
 #include "rub_kernels_staged.cuh"
+#include "rub_kernels_sync.cuh"
 
 using namespace rub;
 
@@ -68,6 +69,8 @@ struct rub_rx {
   cf *d_tw = nullptr;
   unsigned short *d_occ = nullptr;
   float *d_sgn = nullptr;
+  cf *d_s1 = nullptr;  // time-domain access codes [tx][code][n] (timing search)
+  cf *d_s0 = nullptr;  // time-domain S0 (optional)
   unsigned char *d_null = nullptr;
   DemapLut lut;
   WeightMode wm;
@@ -216,6 +219,18 @@ extern "C" rub_status rub_rx_create(rub_rx **out, const rub_config *cfg, const f
   }
   CT(cudaMalloc(&h->d_sgn, sizeof(float) * sgn.size()));
   CT(cudaMemcpy(h->d_sgn, sgn.data(), sizeof(float) * sgn.size(), cudaMemcpyHostToDevice));
+  {
+    // time-domain access codes s1 = IFFT(S1) * sqrt(1/M) (mimo/framing.cc:1228, :1253-1257)
+    std::vector<cf> s1t((size_t)c.N * c.nac * c.M), blk(c.M);
+    const float g1 = (float)sqrt(1.0 / (double)(float)c.M);
+    for (size_t b = 0; b < (size_t)c.N * c.nac; b++) {
+      for (uint32_t k = 0; k < c.M; k++) blk[k] = mk(nul[k] ? 0.f : S1v[2 * (b * c.M + k)], 0.f);
+      host_fft_backward(c.log2M, blk.data(), s1t.data() + b * c.M, packed.data());
+      for (uint32_t k = 0; k < c.M; k++) s1t[b * c.M + k] = cscale(s1t[b * c.M + k], g1);
+    }
+    CT(cudaMalloc(&h->d_s1, sizeof(cf) * s1t.size()));
+    CT(cudaMemcpy(h->d_s1, s1t.data(), sizeof(cf) * s1t.size(), cudaMemcpyHostToDevice));
+  }
   build_demap_lut(c.q, h->lut);
   fill_weight_mode(h);
   CT(cudaMalloc(&h->d_counters, sizeof(uint64_t) * 4 * 8));
@@ -230,7 +245,7 @@ extern "C" void rub_rx_destroy(rub_rx *h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
-  cudaFree(h->d_tw); cudaFree(h->d_occ); cudaFree(h->d_sgn); cudaFree(h->d_null);
+  cudaFree(h->d_tw); cudaFree(h->d_occ); cudaFree(h->d_sgn); cudaFree(h->d_null); cudaFree(h->d_s1); cudaFree(h->d_s0);
   cudaFree(h->d_scratch); cudaFree(h->d_fW); cudaFree(h->d_fG); cudaFree(h->d_counters); cudaFree(h->d_pipe);
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);
   for (auto &e : h->pev) if (e) cudaEventDestroy(e);
@@ -635,4 +650,76 @@ extern "C" rub_status rub_comm_destroy(rub_rx *h) {
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   h->comm = nullptr;
   return RUB_OK;
+}
+
+// ---------------------------------------------------------------- synchronisation -----
+extern "C" rub_status rub_rx_set_S0(rub_rx *h, const float *s0) {
+  if (!h || !s0) return RUB_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (!h->d_s0) CUDA_TRY(cudaMalloc(&h->d_s0, sizeof(cf) * h->h.M));
+  CUDA_TRY(cudaMemcpy(h->d_s0, s0, sizeof(cf) * h->h.M, cudaMemcpyHostToDevice));
+  return RUB_OK;
+}
+
+// framesync::execute_sc_sync(x, stream), mimo/framing.cc:626-637
+extern "C" rub_status rub_rx_sc_metric(rub_rx *h, const float *x, uint64_t n, float *y) {
+  if (!h || !x || !y) { set_error("sc_metric: NULL argument"); return RUB_ERR_INVALID_ARG; }
+  if (n == 0) return RUB_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  cf *dx = nullptr;
+  float *dy = nullptr;
+  CUDA_TRY(cudaMalloc(&dx, sizeof(cf) * n));
+  if (cudaMalloc(&dy, sizeof(float) * n) != cudaSuccess) { cudaFree(dx); set_error("sc_metric: out of device memory"); return RUB_ERR_NOMEM; }
+  rub_status st = RUB_OK;
+  const int M = (int)h->h.M;
+  const size_t smem = (size_t)(M + M / 2 + 256) * sizeof(cf);
+  cudaError_t e = cudaFuncSetAttribute(k_sc_metric, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dx, x, sizeof(cf) * n, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) {
+    k_sc_metric<<<(unsigned)((n + 255) / 256), 256, smem, h->stream>>>(dx, n, M, dy);
+    h->launches += 1;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(y, dy, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) { set_error("sc_metric: %s", cudaGetErrorString(e)); st = RUB_ERR_CUDA; }
+  cudaFree(dx);
+  cudaFree(dy);
+  return st;
+}
+
+// timing search of estimate_channel, mimo/framing.cc:702-744
+extern "C" rub_status rub_rx_timing_search(rub_rx *h, const float *window, uint64_t wlen, int32_t *corr_indices,
+                                           int32_t *s0_corr_index) {
+  if (!h || !window || !corr_indices) { set_error("timing_search: NULL argument"); return RUB_ERR_INVALID_ARG; }
+  const HostCfg &c = h->h;
+  const uint32_t max_ac = c.nac * c.N;
+  // the last candidate window ends at (L-1) + L*max_ac + M (framing.cc:724-727)
+  if (wlen < (uint64_t)c.L * (max_ac + 1) + c.M) { set_error("timing_search: window shorter than the preamble"); return RUB_ERR_INVALID_ARG; }
+  if (s0_corr_index && !h->d_s0) { set_error("timing_search: S0 index requested but rub_rx_set_S0 not called"); return RUB_ERR_INVALID_ARG; }
+  CUDA_TRY(cudaSetDevice(h->device));
+  cf *dw = nullptr;
+  int *di = nullptr;
+  CUDA_TRY(cudaMalloc(&dw, sizeof(cf) * wlen * c.N));
+  if (cudaMalloc(&di, sizeof(int) * (size_t)c.N * (max_ac + 1)) != cudaSuccess) { cudaFree(dw); set_error("timing_search: out of device memory"); return RUB_ERR_NOMEM; }
+  rub_status st = RUB_OK;
+  const size_t smem = (size_t)c.M * sizeof(cf);
+  cudaError_t e = cudaFuncSetAttribute(k_timing_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dw, window, sizeof(cf) * wlen * c.N, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(di, 0, sizeof(int) * (size_t)c.N * (max_ac + 1), h->stream);
+  if (e == cudaSuccess) {
+    dim3 grid(1, c.N * (max_ac + 1));
+    k_timing_search<<<grid, 256, smem, h->stream>>>(dw, wlen, h->d_s1, s0_corr_index ? h->d_s0 : nullptr, (int)c.M,
+                                                    (int)c.L, (int)c.N, (int)c.nac, di, di + (size_t)c.N * max_ac);
+    h->launches += 1;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(corr_indices, di, sizeof(int) * (size_t)c.N * max_ac, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess && s0_corr_index)
+    e = cudaMemcpyAsync(s0_corr_index, di + (size_t)c.N * max_ac, sizeof(int) * c.N, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) { set_error("timing_search: %s", cudaGetErrorString(e)); st = RUB_ERR_CUDA; }
+  cudaFree(dw);
+  cudaFree(di);
+  return st;
 }
