@@ -16,7 +16,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librubmimo_b200.so")
+LIB_PATH = os.environ.get("RUB_MIMO_LIB") or os.path.join(_HERE, "librubmimo_b200.so")  # override: A/B builds
 
 # ---- constants mirrored from include/rub_mimo/rub_mimo.h -------------------------------
 OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_NO_DEVICE, ERR_CUDA, ERR_NOMEM, ERR_NCCL, ERR_IO = range(8)

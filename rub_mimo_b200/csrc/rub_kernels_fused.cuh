@@ -116,6 +116,11 @@ __device__ __forceinline__ float2 ld_hint2(const void *p, unsigned long long pol
                : "l"(p), "l"(pol));
   return v;
 }
+__device__ __forceinline__ float ld_hint1(const void *p, unsigned long long pol) {
+  float v;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+  return v;
+}
 __device__ __forceinline__ unsigned ld_hint_u16(const void *p, unsigned long long pol) {
   unsigned short v;
   asm volatile("ld.global.L1::no_allocate.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(v) : "l"(p), "l"(pol));
@@ -168,6 +173,7 @@ struct WarpCtx {
   unsigned char *slot0;  // this warp's first staging slot (the second follows stage_stride bytes later)
   int stage_stride;
   int koff;              // first carrier of this lane: warp*64 + 2*lane
+  int kw;                // first carrier of this warp (warp-uniform)
 };
 
 template <int N, int M>
@@ -254,6 +260,51 @@ __device__ __forceinline__ void task_compute(const TaskRegs<N> &t, const ChainAr
   }
 }
 
+// Q bytes (8 symbols, MSB first) from hi = the first 4 symbols (4Q/2 bits each... 4*Q/2 = 2Q bits... see callers)
+// and lo = the next 4: byte order fixed with PRMT
+template <int Q>
+__device__ __forceinline__ void store_packed_bits(unsigned char *bp, unsigned hi, unsigned lo) {
+  if (Q == 2) {         // 8 + 8 bits
+    *reinterpret_cast<unsigned short *>(bp) = (unsigned short)__byte_perm(hi, lo, 0x4440);   // [hi.b0, lo.b0]
+  } else if (Q == 4) {  // 16 + 16 bits
+    *reinterpret_cast<unsigned *>(bp) = __byte_perm(hi, lo, 0x4501);                         // [hi.b1, hi.b0, lo.b1, lo.b0]
+  } else if (Q == 6) {  // 24 + 24 bits, 2-byte aligned
+    unsigned short *b16 = reinterpret_cast<unsigned short *>(bp);
+    b16[0] = (unsigned short)__byte_perm(hi, lo, 0x4412);  // [hi.b2, hi.b1]
+    b16[1] = (unsigned short)__byte_perm(hi, lo, 0x4460);  // [hi.b0, lo.b2]
+    b16[2] = (unsigned short)__byte_perm(hi, lo, 0x4445);  // [lo.b1, lo.b0]
+  } else {              // 32 + 32 bits
+    *reinterpret_cast<uint2 *>(bp) = make_uint2(__byte_perm(hi, 0, 0x0123), __byte_perm(lo, 0, 0x0123));
+  }
+}
+
+// packed per-lane error counters: one byte per stream, four streams per word
+template <int N> struct ErrWords { static constexpr int NW = (N + 3) / 4; };
+
+// adds this warp's packed per-lane error counts to the CTA counters cnt[N][2] = {bit errors, symbol errors}
+template <int N>
+__device__ __forceinline__ void flush_counts(const unsigned *eb, const unsigned *es, unsigned *cnt) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int w = 0; w < ErrWords<N>::NW; w++) {
+    // bytes -> 16-bit fields so that the sum over 32 lanes cannot overflow
+    const unsigned b_even = __reduce_add_sync(0xffffffffu, eb[w] & 0x00ff00ffu);         // streams 4w, 4w+2
+    const unsigned s_even = __reduce_add_sync(0xffffffffu, es[w] & 0x00ff00ffu);
+    unsigned b_odd = 0, s_odd = 0;
+    if (N > 1) {
+      b_odd = __reduce_add_sync(0xffffffffu, (eb[w] >> 8) & 0x00ff00ffu);                // streams 4w+1, 4w+3
+      s_odd = __reduce_add_sync(0xffffffffu, (es[w] >> 8) & 0x00ff00ffu);
+    }
+    const int first = 8 * w;  // cnt index of stream 4w
+    if (lane < 8 && first + lane < 2 * N) {
+      const int st = lane >> 1;
+      const unsigned even = (lane & 1) ? s_even : b_even, odd = (lane & 1) ? s_odd : b_odd;
+      const unsigned v = (((st & 1) ? odd : even) >> (16 * (st >> 1))) & 0xffffu;
+      atomicAdd(cnt + first + lane, v);
+    }
+  }
+}
+
 // detection of one payload OFDM symbol by the whole CTA; `cur` already holds task 0.
 // A warp walks KPW blocks of 64 carriers; for each block it reads Y once (N x 16 B per lane) and
 // serves the N streams one after the other.
@@ -326,7 +377,8 @@ __global__ void __launch_bounds__(FusedTraits<LOG2M, N>::THREADS) k_rx_fused(Fus
   unsigned long long *mbar = reinterpret_cast<unsigned long long *>(txbuf + 2 * N * M);  // full[2], empty[2]
   unsigned *cnt = reinterpret_cast<unsigned *>(mbar + 4);  // [N][2] bit errors, symbol errors
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform for the compiler
   const int ant = tid / NT, ft = tid % NT;
   const int nsym = a.T + a.D;
   const int q = a.q;
@@ -353,7 +405,8 @@ __global__ void __launch_bounds__(FusedTraits<LOG2M, N>::THREADS) k_rx_fused(Fus
 
   // detection constants of this warp / lane
   WarpCtx wc;
-  wc.koff = warp * 64 + 2 * lane;
+  wc.kw = warp * 64;
+  wc.koff = wc.kw + 2 * lane;
   wc.Wp = Wc + wc.koff;
   wc.gp = gc + wc.koff;
   wc.slot0 = stage_base + (size_t)(warp * 2) * stage_stride;
@@ -491,11 +544,12 @@ __global__ void __launch_bounds__(FusedTraits<LOG2M, N>::THREADS) k_rx_fused(Fus
       }
     } else {
       // ---------------- detect + demap + count ----------------
+#define DETECT(MBV) detect_symbol<LOG2M, N, MBV>(fa, cur, wc, buf, txbuf + (g & 1) * N * M, symbase, lut, refs, pol_keep, pol_stream, cnt)
       switch (q) {
-        case 2: detect_symbol<LOG2M, N, 1>(fa, cur, wc, buf, txbuf + (g & 1) * N * M, symbase, lut, refs, pol_keep, pol_stream, cnt); break;
-        case 4: detect_symbol<LOG2M, N, 2>(fa, cur, wc, buf, txbuf + (g & 1) * N * M, symbase, lut, refs, pol_keep, pol_stream, cnt); break;
-        case 6: detect_symbol<LOG2M, N, 3>(fa, cur, wc, buf, txbuf + (g & 1) * N * M, symbase, lut, refs, pol_keep, pol_stream, cnt); break;
-        default: detect_symbol<LOG2M, N, 4>(fa, cur, wc, buf, txbuf + (g & 1) * N * M, symbase, lut, refs, pol_keep, pol_stream, cnt); break;
+        case 2: DETECT(1); break;
+        case 4: DETECT(2); break;
+        case 6: DETECT(3); break;
+        default: DETECT(4); break;
       }
       release_buf();
     }
@@ -516,24 +570,28 @@ __global__ void __launch_bounds__(FusedTraits<LOG2M, N>::THREADS) k_rx_fused(Fus
 
 
 // ---------------------------------------------------------------------------------------------
-// k_detect_blocks: detection for the staged path when every carrier is occupied (e.g. C4, 8x8 /
-// 4096, whose 256 KB of FFT output per symbol does not fit one CTA's shared memory).  Same lane
-// mapping, per-task code and TMA bulk stores as the fused kernel, but Y, W, gain, isig and
-// tx_data come from HBM/L2 (written by k_fft_staged / k_weights).  One warp per (frame, symbol,
-// 64-carrier block); it reads Y once and serves the N streams in turn.
+// k_detect_lean: detection for the staged path when every carrier is occupied (e.g. C4, 8x8 /
+// 4096, whose 256 KB of FFT output per symbol does not fit one CTA's shared memory).  Y, W, gain,
+// isig and tx_data come from HBM/L2 (written by k_fft_staged / k_weights).  One warp per (frame,
+// symbol, 64-carrier block); it reads Y once and serves the N streams in turn, one carrier per
+// lane (two half-tasks of 32 carriers per stream): a thread then needs ~80 registers for N = 4,
+// an SM holds 24 warps instead of the 16 a two-carriers-per-lane mapping allows, and the
+// W/gain/isig/tx loads of the next half-task are in flight while the current one is computed.
+// LLRs and packed bits are staged per warp in their final byte order and leave by TMA bulk store.
 template <int N, int MB>
-__global__ void __launch_bounds__(128) k_detect_blocks(ChainArgs a, DemapLut lutp, int llr_stage_bytes) {
-  constexpr int Q = 2 * MB;
+__global__ void __launch_bounds__(256, (N <= 4 ? 3 : 2)) k_detect_lean(ChainArgs a, DemapLut lutp, int llr_stage_bytes) {
+  constexpr int Q = 2 * MB, PL = 1 << MB, WARPS = 8;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ float2 lut[64];
   __shared__ unsigned cnt[2 * N];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   if (tid < 64) lut[tid] = make_float2(lutp.slope[tid], lutp.icpt[tid]);
   if (tid < 2 * N) cnt[tid] = 0;
   __syncthreads();
   const int M = a.M;
   const int blocks_per_sym = M / 64;
-  const long long wid = (long long)blockIdx.x * 4 + warp;            // (frame, symbol, block)
+  const long long wid = (long long)blockIdx.x * WARPS + warp;            // (frame, symbol, block)
   const long long nwork = (long long)a.n_frames * a.D * blocks_per_sym;
   const unsigned long long pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
   float refs[4];
@@ -543,47 +601,104 @@ __global__ void __launch_bounds__(128) k_detect_blocks(ChainArgs a, DemapLut lut
     const int kb = (int)(wid % blocks_per_sym);
     const int d = (int)((wid / blocks_per_sym) % a.D);
     const long long frame = wid / ((long long)blocks_per_sym * a.D);
-    const int k = kb * 64 + 2 * lane;
+    const int k0 = kb * 64;
     const long long nsym = a.T + a.D;
-    const cf *Yf = a.Y + ((frame * nsym + a.T + d) * N) * M + k;
-    const cf *Wf = a.W + frame * N * N * M + k;
-    const float *gf = a.gain + frame * N * M + k, *sf = a.isig + frame * N * M + k;
-    float4 y4[N];
-#pragma unroll
-    for (int r = 0; r < N; r++) y4[r] = ld_hint4(Yf + (long long)r * M, pol_stream);
+    const cf *Yf = a.Y + ((frame * nsym + a.T + d) * N) * M + k0 + lane;
+    const cf *Wf = a.W + frame * N * N * M + k0 + lane;
+    const float *gf = a.gain + frame * N * M + k0 + lane, *sf = a.isig + frame * N * M + k0 + lane;
     const int stage_stride = llr_stage_bytes + 64;
     const long long DM = (long long)a.D * M;
-    const long long obase = (frame * N * a.D + d) * (long long)M + k;
-#pragma unroll 1
-    for (int s = 0; s < N; s++) {
-      TaskRegs<N> t;
+    const long long obase = (frame * N * a.D + d) * (long long)M + k0;   // warp-uniform
+    float2 y[2][N];
 #pragma unroll
-      for (int r = 0; r < N; r++) t.w[r] = ld_hint4(Wf + (long long)(s * N + r) * M, pol_keep);
-      t.g = ld_hint2(gf + (long long)s * M, pol_keep);
-      t.is = ld_hint2(sf + (long long)s * M, pol_keep);
+    for (int h = 0; h < 2; h++)
+#pragma unroll
+      for (int r = 0; r < N; r++) y[h][r] = ld_hint2(Yf + (long long)r * M + 32 * h, pol_stream);
+    unsigned eb[ErrWords<N>::NW] = {}, es[ErrWords<N>::NW] = {};
+    const bool want_llr = a.llr != nullptr;
+    // half-task j = (stream j/2, carriers k0 + 32*(j%2) + lane); the loads of half-task j+1 are
+    // in flight while j is computed
+    struct HalfRegs { float2 w[N]; float g, is; unsigned tx; };
+    auto load_half = [&](HalfRegs &t, int j) {
+      const int s = j >> 1, h = j & 1;
+#pragma unroll
+      for (int r = 0; r < N; r++) t.w[r] = ld_hint2(Wf + (long long)(s * N + r) * M + 32 * h, pol_keep);
+      t.g = ld_hint1(gf + (long long)s * M + 32 * h, pol_keep);
+      t.is = ld_hint1(sf + (long long)s * M + 32 * h, pol_keep);
+      t.tx = a.tx_data ? (unsigned)a.tx_data[obase + s * DM + 32 * h + lane] : 0u;
+    };
+    HalfRegs cur, nxt;
+    load_half(cur, 0);
+    unsigned symh[2] = {0u, 0u};
+#pragma unroll
+    for (int j = 0; j < 2 * N; j++) {
+      const int s = j >> 1, h = j & 1;
+      if (j + 1 < 2 * N) load_half(nxt, j + 1);
       unsigned char *slot = smem_raw + (size_t)(warp * 2 + (s & 1)) * stage_stride;
-      if (lane == 0) bulk_wait_read<1>();
-      __syncwarp();
-      const long long o = obase + s * DM;
-      // task_compute reads the transmitted symbols through a pointer: global memory works too
-      task_compute<N, MB>(t, a, y4, o, reinterpret_cast<float *>(slot) + lane * 2 * Q,
-                          slot + llr_stage_bytes + (lane >> 2) * Q, lut, refs, pol_stream,
-                          a.tx_data ? ld_hint_u16(a.tx_data + o, pol_stream) : 0u, cnt + 2 * s);
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        const long long ob = o - 2 * lane;
-        if (a.llr) bulk_store(a.llr + ob * Q, slot, (unsigned)(64 * Q * 4), pol_stream);
-        if (a.bits) bulk_store(a.bits + (ob >> 3) * Q, slot + llr_stage_bytes, (unsigned)(8 * Q), pol_stream);
-        bulk_commit();
+      if (h == 0) {
+        if (lane == 0) bulk_wait_read<1>();
+        __syncwarp();
       }
+      cf acc = mk(0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r < N; r++) acc = cmac(acc, mk(cur.w[r].x, cur.w[r].y), mk(y[h][r].x, y[h][r].y));
+      const cf z = cscale(acc, cur.g);
+      const unsigned si = slice_axis_refs<MB>(z.x, refs), sq = slice_axis_refs<MB>(z.y, refs);
+      const unsigned c = (si << MB) | sq;
+      symh[h] = c ^ ((c >> 1) & ~(1u << (MB - 1)));
+      const long long o = obase + s * DM + 32 * h + lane;
+      if (a.eq) st_hint2(a.eq + o, make_float2(z.x, z.y), pol_stream);
+      if (a.rx_data) a.rx_data[o] = (unsigned char)symh[h];
+      if (want_llr) {
+        const float2 *li = lut + si, *lq = lut + sq;
+        float2 *lp = reinterpret_cast<float2 *>(slot) + (32 * h + lane) * MB;
+        float l[Q];
+#pragma unroll
+        for (int b = 0; b < MB; b++) {
+          const float2 ci = li[b * PL], cq = lq[b * PL];
+          l[b] = fmaf(ci.x, z.x, ci.y) * cur.is;
+          l[MB + b] = fmaf(cq.x, z.y, cq.y) * cur.is;
+        }
+#pragma unroll
+        for (int b = 0; b < MB; b++) lp[b] = make_float2(l[2 * b], l[2 * b + 1]);
+      }
+      if (a.tx_data) {
+        const unsigned x = symh[h] ^ cur.tx;
+        eb[s >> 2] += (unsigned)__popc(x) << (8 * (s & 3));
+        es[s >> 2] += (unsigned)(x != 0u) << (8 * (s & 3));
+      }
+      if (h == 1) {
+        if (a.bits) {
+          // lane L holds symbols k0+L and k0+32+L; 8 consecutive symbols = Q bytes, MSB first
+#pragma unroll
+          for (int hh = 0; hh < 2; hh++) {
+            const unsigned v1 = symh[hh];
+            const unsigned p1 = __shfl_down_sync(0xffffffffu, v1, 1);
+            const unsigned v2 = (v1 << Q) | p1;                       // lanes 0 mod 2: 2 symbols
+            const unsigned p2 = __shfl_down_sync(0xffffffffu, v2, 2);
+            const unsigned v4 = (v2 << (2 * Q)) | p2;                 // lanes 0 mod 4: 4 symbols
+            const unsigned p4 = __shfl_down_sync(0xffffffffu, v4, 4);
+            if ((lane & 7) == 0) store_packed_bits<Q>(slot + llr_stage_bytes + (4 * hh + (lane >> 3)) * Q, v4, p4);
+          }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          const long long ob = obase + s * DM;
+          if (a.llr) bulk_store(a.llr + ob * Q, slot, (unsigned)(64 * Q * 4), pol_stream);
+          if (a.bits) bulk_store(a.bits + (ob >> 3) * Q, slot + llr_stage_bytes, (unsigned)(8 * Q), pol_stream);
+          bulk_commit();
+        }
+      }
+      if (j + 1 < 2 * N) cur = nxt;
     }
+    if (a.tx_data) flush_counts<N>(eb, es, cnt);
     if (lane == 0) bulk_wait_all();
   }
   __syncthreads();
   if (a.tx_data && a.counters && tid < N) {
-    const long long w0 = (long long)blockIdx.x * 4;
-    const long long nw = nwork - w0 < 4 ? nwork - w0 : 4;  // warps of this CTA that had work
+    const long long w0 = (long long)blockIdx.x * WARPS;
+    const long long nw = nwork - w0 < WARPS ? nwork - w0 : WARPS;  // warps of this CTA that had work
     if (nw > 0) {
       atomicAdd(&a.counters[tid * 4 + 0], (unsigned long long)cnt[2 * tid]);
       atomicAdd(&a.counters[tid * 4 + 1], (unsigned long long)nw * 64 * a.q);

@@ -326,14 +326,14 @@ static void launch_fft(const ChainArgs &a, cudaStream_t st, cudaError_t *err) {
   k_fft_staged<LOG2M, F><<<grid, NT * F, smem, st>>>(a);
 }
 template <int N, int MB>
-static void launch_detect_blocks(const ChainArgs &a, const rub_rx *h, cudaStream_t st) {
+static void launch_detect_lean(const ChainArgs &a, const rub_rx *h, cudaStream_t st) {
   const int llr_stage = 256 * 2 * MB;
-  const size_t smem = (size_t)4 * 2 * (llr_stage + 64);
+  const size_t smem = (size_t)8 * 2 * (llr_stage + 64);  // 8 warps x 2 staging slots
   const long long nwork = (long long)a.n_frames * a.D * (a.M / 64);
-  k_detect_blocks<N, MB><<<(unsigned)((nwork + 3) / 4), 128, smem, st>>>(a, h->lut, llr_stage);
+  k_detect_lean<N, MB><<<(unsigned)((nwork + 7) / 8), 256, smem, st>>>(a, h->lut, llr_stage);
 }
 // block-mapped detect kernel: all carriers occupied, 16-byte aligned outputs, N in {1,2,4,8}
-static bool detect_blocks_ok(const ChainArgs &a) {
+static bool detect_lean_ok(const ChainArgs &a) {
   if (a.Mo != a.M || (a.M % 64)) return false;
   if (!(a.N == 1 || a.N == 2 || a.N == 4 || a.N == 8)) return false;
   if (((uintptr_t)a.llr & 15) || ((uintptr_t)a.bits & 15) || ((uintptr_t)a.eq & 15)) return false;
@@ -346,12 +346,12 @@ static void launch_weights_detect(const ChainArgs &a, const rub_rx *h, cudaStrea
   k_weights<N><<<(unsigned)((tw + 127) / 128), 128, 0, st>>>(a, h->wm);
   if (e0) cudaEventRecord(e0, st);
   if constexpr (N == 1 || N == 2 || N == 4 || N == 8) {
-    if (detect_blocks_ok(a)) {
+    if (detect_lean_ok(a)) {
       switch (a.q) {
-        case 2: launch_detect_blocks<N, 1>(a, h, st); break;
-        case 4: launch_detect_blocks<N, 2>(a, h, st); break;
-        case 6: launch_detect_blocks<N, 3>(a, h, st); break;
-        default: launch_detect_blocks<N, 4>(a, h, st); break;
+        case 2: launch_detect_lean<N, 1>(a, h, st); break;
+        case 4: launch_detect_lean<N, 2>(a, h, st); break;
+        case 6: launch_detect_lean<N, 3>(a, h, st); break;
+        default: launch_detect_lean<N, 4>(a, h, st); break;
       }
       if (e1) cudaEventRecord(e1, st);
       return;
