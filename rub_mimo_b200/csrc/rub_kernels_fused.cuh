@@ -541,6 +541,7 @@ __global__ void __launch_bounds__(FusedTraits<LOG2M, N>::THREADS) k_rx_fused(Fus
 #pragma unroll
           for (int s = 0; s < N; s++) { st_hint1(gc + (size_t)s * M + k, gain[s], pol_keep); st_hint1(ic + (size_t)s * M + k, isig[s], pol_keep); }
         }
+        __syncthreads();  // W complete before any warp prefetches it for the first payload symbol
       }
     } else {
       // ---------------- detect + demap + count ----------------

@@ -11,6 +11,7 @@
 
 #include "rub_internal.h"
 #include "rub_kernels_fused.cuh"
+#include "rub_kernels_fused32.cuh"
 #include "rub_kernels_staged.cuh"
 #include "rub_kernels_sync.cuh"
 
@@ -81,6 +82,7 @@ struct rub_rx {
   cf *d_fW = nullptr;
   float *d_fG = nullptr;
   int fused_grid = 0;
+  bool fused32 = false;  // 32-warp variant of the fused kernel (rub_kernels_fused32.cuh)
   size_t fused_smem = 0;
   bool fused_ready = false;
   uint64_t *d_counters = nullptr;
@@ -115,6 +117,21 @@ static void fused_launch(int grid, size_t smem, cudaStream_t st, const FusedArgs
   k_rx_fused<LOG2M, N><<<grid, FusedTraits<LOG2M, N>::THREADS, smem, st>>>(fa, lut);
 }
 
+template <int LOG2M, int N>
+static rub_status fused32_prepare(rub_rx *h, size_t *smem_out, int *grid_out) {
+  using TR = Fused32Traits<LOG2M, N>;
+  const size_t smem = TR::smem_bytes((int)h->h.q);
+  CUDA_TRY(cudaFuncSetAttribute(k_rx_fused32<LOG2M, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_rx_fused32<LOG2M, N>, TR::THREADS, smem));
+  if (occ < 1) { set_error("fused32 kernel does not fit (smem %zu B)", smem); return RUB_ERR_UNSUPPORTED; }
+  *smem_out = smem;
+  *grid_out = occ * h->num_sms;
+  return RUB_OK;
+}
+// the 32-warp variant exists for the configurations where it wins
+static bool fused32_has_instance(uint32_t l2, uint32_t N) { return l2 == 11 && N == 4; }
+
 // the (log2 M, N) pairs the fused kernel is instantiated for
 #define RUB_FUSED_LIST(X) X(9, 2) X(9, 4) X(10, 2) X(10, 4) X(11, 1) X(11, 2) X(11, 4) X(12, 1) X(12, 2)
 
@@ -125,12 +142,14 @@ static bool fused_has_instance(uint32_t l2, uint32_t N) {
   return false;
 }
 static rub_status fused_prepare_dispatch(rub_rx *h, size_t *smem, int *grid) {
+  if (h->fused32) return fused32_prepare<11, 4>(h, smem, grid);
 #define X(L, NN) if (h->h.log2M == L && h->h.N == NN) return fused_prepare<L, NN>(h, smem, grid);
   RUB_FUSED_LIST(X)
 #undef X
   return RUB_ERR_UNSUPPORTED;
 }
 static void fused_launch_dispatch(rub_rx *h, int grid, size_t smem, const FusedArgs &fa) {
+  if (h->fused32) { k_rx_fused32<11, 4><<<grid, Fused32Traits<11, 4>::THREADS, smem, h->stream>>>(fa, h->lut); return; }
 #define X(L, NN) if (h->h.log2M == L && h->h.N == NN) { fused_launch<L, NN>(grid, smem, h->stream, fa, h->lut); return; }
   RUB_FUSED_LIST(X)
 #undef X
@@ -441,6 +460,7 @@ static rub_status run_staged(rub_rx *h, ChainArgs a, const rub_rx_io *io, uint32
 static rub_status run_fused(rub_rx *h, const ChainArgs &a, uint32_t n_frames, bool timed) {
   const HostCfg &c = h->h;
   if (!h->fused_ready) {
+    h->fused32 = fused32_has_instance(c.log2M, c.N) && getenv("RUB_FUSED32") != nullptr;
     int grid = 0;
     size_t smem = 0;
     rub_status st = fused_prepare_dispatch(h, &smem, &grid);
