@@ -270,6 +270,19 @@ uint32_t rub_framegen_write_comb_words(rub_framegen *fg, float *const *tx_buff);
 uint32_t rub_framegen_assemble_mimo_packet(rub_framegen *fg, float *const *tx_buff,
                                            const float *const *in_buff);
 
+/* Batched transmit waveform on the GPU: the access codes of
+ * framegen::write_sync_words (framing.cc:191-204; S0 is not written) followed by
+ * framegen::assemble_mimo_packet (framing.cc:210-235) for every payload symbol, for whole
+ * batches of frames: symbol indices -> modulate -> carrier mapping -> IFFT ->
+ * dft_normalizer -> cyclic prefix -> * baseband_gain.  Bit-identical to rub_framegen_*.
+ * `ctx` supplies the device, stream and tables (any receiver handle of the same config).
+ * tx_data: DEVICE [n_frames][N][D][Mo] symbol indices.  out: DEVICE complex64, sample n of
+ * (frame f, stream s) at out[2*(f*frame_stride + s*stream_stride + n)], strides in complex
+ * samples, (T + D)*(M + cp) samples written per row.  Asynchronous on the handle's stream. */
+rub_status rub_framegen_batch_device(rub_rx *ctx, const uint8_t *tx_data, uint32_t n_frames,
+                                     float *out, uint64_t frame_stride, uint64_t stream_stride,
+                                     float baseband_gain);
+
 /* --------------------------------------------- synthetic / offline IQ source -------- */
 /* Replaces the USRP stream (mimo/main.cc:872-898) with a synthetic source: for each
  * frame, random symbol indices -> modulate -> framegen -> BASEBAND_GAIN -> per-link
@@ -302,6 +315,33 @@ rub_status rub_file_read_fc32(const char *path, float *dst, uint64_t max_samples
                               uint64_t *n_read);
 rub_status rub_file_write_fc32(const char *path, const float *src, uint64_t n_samples);
 rub_status rub_file_write_u32(const char *path, const uint32_t *src, uint64_t n);
+
+/* Offline IQ-file driver: the seam of mimo/main.cc:906-918, where the
+ * reference reads "/tmp/rx%d.dat" instead of the USRP, with the sinks of :1413-1419.
+ * One fc32 capture per rx antenna; frame f of every file starts at complex sample
+ * first_sample + f*frame_stride.  The files are read in chunks into two pinned staging slots by a
+ * reader thread while the previous chunk is on the GPU (rub_rx_process_batch_host pipelines its
+ * H2D / kernels / D2H inside a chunk), and the requested outputs are appended to the sinks.
+ * Any path array / path may be NULL.  Sinks per stream s: eq_paths[s] fc32 equalised symbols
+ * ("rx_sig%d.dat"), rx_data_paths[s] uint32 decisions ("rx_data%d.dat"); tx_data_paths[s] is a
+ * uint32 input of transmitted symbol indices, D*Mo per frame ("tx_data%d.dat"), enabling the
+ * error counters.  llr_path / bits_path receive the batch layout of rub_rx_io, frame-major.   */
+typedef struct rub_file_job {
+  uint32_t struct_size;
+  uint32_t n_frames;
+  uint64_t first_sample;
+  uint64_t frame_stride;            /* 0 = (T+D)*(M+cp): frames back to back                 */
+  const char *const *rx_paths;      /* [N]                                                    */
+  const char *const *tx_data_paths; /* [N] or NULL                                            */
+  const char *const *eq_paths;      /* [N] or NULL                                            */
+  const char *const *rx_data_paths; /* [N] or NULL                                            */
+  const char *llr_path;             /* or NULL                                                */
+  const char *bits_path;            /* or NULL                                                */
+  uint32_t chunk_frames;            /* frames per staging slot, 0 = about 64 MB of input      */
+} rub_file_job;
+/* frames_done (may be NULL) = frames fully processed; a capture shorter than n_frames is
+ * not an error, the run stops at the last complete frame.                                    */
+rub_status rub_rx_process_files(rub_rx *h, const rub_file_job *job, uint64_t *frames_done);
 
 /* ------------------------------------------------------------- misc ---------------- */
 const char *rub_strerror(rub_status s);

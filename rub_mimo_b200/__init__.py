@@ -61,6 +61,14 @@ class rub_msequence(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("m", "g", "a", "n", "v", "b")]
 
 
+class rub_file_job(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("n_frames", C.c_uint32), ("first_sample", C.c_uint64),
+                ("frame_stride", C.c_uint64), ("rx_paths", C.POINTER(C.c_char_p)),
+                ("tx_data_paths", C.POINTER(C.c_char_p)), ("eq_paths", C.POINTER(C.c_char_p)),
+                ("rx_data_paths", C.POINTER(C.c_char_p)), ("llr_path", C.c_char_p), ("bits_path", C.c_char_p),
+                ("chunk_frames", C.c_uint32)]
+
+
 class rub_synth_params(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("first_frame", C.c_uint64), ("n_taps", C.c_uint32),
                 ("snr_db", C.c_float), ("baseband_gain", C.c_float), ("fixed_H", C.c_void_p),
@@ -73,7 +81,8 @@ ABI_SYMBOLS = [
     "rub_rx_create", "rub_rx_destroy", "rub_rx_process_batch", "rub_rx_process_batch_host",
     "rub_rx_sync", "rub_rx_set_path", "rub_rx_get_path", "rub_rx_reset_counters",
     "rub_rx_device_counters", "rub_rx_read_counters", "rub_rx_launch_count", "rub_rx_last_timing",
-    "rub_rx_algorithmic_bytes", "rub_rx_sc_metric", "rub_rx_timing_search", "rub_rx_set_S0", "rub_comm_get_unique_id", "rub_comm_init", "rub_allreduce_counters",
+    "rub_rx_algorithmic_bytes", "rub_rx_sc_metric", "rub_rx_timing_search", "rub_rx_set_S0",
+    "rub_framegen_batch_device", "rub_rx_process_files", "rub_comm_get_unique_id", "rub_comm_init", "rub_allreduce_counters",
     "rub_comm_destroy", "rub_shard_range", "rub_msequence_init", "rub_msequence_reset",
     "rub_msequence_advance", "rub_msequence_generate_symbol", "rub_ofdmframe_init_default_sctype",
     "rub_ofdmframe_validate_sctype", "rub_ofdmframe_init_S0", "rub_ofdmframe_init_S1",
@@ -138,6 +147,8 @@ def lib():
         L.rub_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.rub_rx_sc_metric.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         L.rub_rx_timing_search.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.rub_framegen_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64,
+                                                C.c_uint64, C.c_float]
         L.rub_rx_set_S0.argtypes = [C.c_void_p, C.c_void_p]
         L.rub_framegen_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.rub_framegen_destroy.argtypes = [C.c_void_p]
@@ -540,6 +551,43 @@ class Receiver:
         io.counters = counters.ctypes.data if counters is not None else None
         io.out_mask = out_mask
         _check(lib().rub_rx_process_batch_host(self.h, C.byref(io), n_frames))
+        return out
+
+    # -- offline IQ-file driver (f3) --
+    def process_files(self, rx_paths, n_frames, first_sample=0, frame_stride=0, tx_data_paths=None, eq_paths=None,
+                      rx_data_paths=None, llr_path=None, bits_path=None, chunk_frames=0):
+        """mimo/main.cc:906-918 seam: per-antenna fc32 captures in, the reference's sinks out.
+        Returns the number of complete frames processed."""
+        def arr(paths):
+            if paths is None:
+                return None
+            assert len(paths) == self.cfg.N
+            return (C.c_char_p * len(paths))(*[str(p).encode() for p in paths])
+        keep = [arr(rx_paths), arr(tx_data_paths), arr(eq_paths), arr(rx_data_paths)]
+        job = rub_file_job(C.sizeof(rub_file_job), n_frames, first_sample, frame_stride, keep[0], keep[1], keep[2],
+                           keep[3], None if llr_path is None else str(llr_path).encode(),
+                           None if bits_path is None else str(bits_path).encode(), chunk_frames)
+        done = C.c_uint64()
+        _check(lib().rub_rx_process_files(self.h, C.byref(job), C.byref(done)))
+        return done.value
+
+    # -- transmit side (f4) --
+    def framegen_batch(self, tx_data, baseband_gain=1.0):
+        """Batched framegen (mimo/framing.cc:191-235) on the GPU.  tx_data: CUDA uint8 tensor
+        [F][N][D][Mo]; returns a CUDA complex64 tensor [F][N][(T+D)*L] (access codes + payload)."""
+        import torch
+        cfg = self.cfg
+        assert tx_data.is_cuda and tx_data.dtype == torch.uint8 and tx_data.is_contiguous()
+        F = tx_data.shape[0]
+        assert tuple(tx_data.shape) == (F, cfg.N, cfg.D, cfg.Mo)
+        row = (cfg.T + cfg.D) * cfg.L
+        out = torch.empty((F, cfg.N, row), dtype=torch.complex64, device=tx_data.device)
+        if self.tstream is not None:
+            self.tstream.wait_stream(torch.cuda.current_stream())
+        _check(lib().rub_framegen_batch_device(self.h, C.c_void_p(tx_data.data_ptr()), F, C.c_void_p(out.data_ptr()),
+                                               cfg.N * row, row, C.c_float(baseband_gain)))
+        if self.tstream is not None:
+            torch.cuda.current_stream().wait_stream(self.tstream)
         return out
 
     # -- synchronisation rows (f1/f2) --

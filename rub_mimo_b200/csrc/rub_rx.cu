@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <thread>
 #include <vector>
 
 #include "rub_internal.h"
@@ -14,6 +15,7 @@
 #include "rub_kernels_fused32.cuh"
 #include "rub_kernels_staged.cuh"
 #include "rub_kernels_sync.cuh"
+#include "rub_kernels_tx.cuh"
 
 using namespace rub;
 
@@ -741,5 +743,180 @@ extern "C" rub_status rub_rx_timing_search(rub_rx *h, const float *window, uint6
   if (e != cudaSuccess) { set_error("timing_search: %s", cudaGetErrorString(e)); st = RUB_ERR_CUDA; }
   cudaFree(dw);
   cudaFree(di);
+  return st;
+}
+
+// ---------------------------------------------------------------- transmit side -------
+// framegen::write_sync_words access codes + assemble_mimo_packet, mimo/framing.cc:191-235
+extern "C" rub_status rub_framegen_batch_device(rub_rx *h, const uint8_t *tx_data, uint32_t n_frames, float *out,
+                                                uint64_t frame_stride, uint64_t stream_stride, float baseband_gain) {
+  if (!h || !tx_data || !out) { set_error("framegen_batch: NULL argument"); return RUB_ERR_INVALID_ARG; }
+  if (n_frames == 0) return RUB_OK;
+  const HostCfg &c = h->h;
+  const uint64_t row = (uint64_t)(c.T + c.D) * c.L;
+  if (stream_stride < row || frame_stride < stream_stride * (c.N - 1) + row) {
+    set_error("framegen_batch: strides smaller than a row of %llu samples", (unsigned long long)row);
+    return RUB_ERR_INVALID_ARG;
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  TxArgs a;
+  a.tx_data = tx_data;
+  a.out = reinterpret_cast<cf *>(out);
+  a.frame_stride = (long long)frame_stride;
+  a.stream_stride = (long long)stream_stride;
+  a.tw = h->d_tw; a.occ = h->d_occ; a.scnull = h->d_null; a.sgn = h->d_sgn; a.s1 = h->d_s1;
+  a.n_frames = (int)n_frames; a.N = (int)c.N; a.nac = (int)c.nac; a.T = (int)c.T; a.D = (int)c.D;
+  a.M = (int)c.M; a.Mo = (int)c.Mo; a.cp = (int)c.cp; a.L = (int)c.L; a.q = (int)c.q; a.P = (int)c.P;
+  a.comb = c.c.estimator == RUB_EST_LS_COMB_INTERP;
+  a.alpha = c.alpha; a.dn = c.dn; a.g1 = (float)sqrt(1.0 / (double)(float)c.M); a.gain = baseband_gain;
+  const long long ctas = (long long)n_frames * (c.T + c.D) * c.N;
+  if (ctas > 0x7fffffffLL) { set_error("framegen_batch: batch too large"); return RUB_ERR_INVALID_ARG; }
+  switch (c.log2M) {
+#define X(L2)                                                                                              \
+  case L2: {                                                                                               \
+    const size_t smem = (size_t)2 * fft_padded_size(1 << L2) * sizeof(cf);                                 \
+    CUDA_TRY(cudaFuncSetAttribute(k_framegen<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_framegen<L2><<<(unsigned)ctas, FftPlan<L2>::NT, smem, h->stream>>>(a);                               \
+  } break;
+    X(6) X(7) X(8) X(9) X(10) X(11) X(12)
+#undef X
+    default: set_error("framegen_batch: unsupported M"); return RUB_ERR_UNSUPPORTED;
+  }
+  h->launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return RUB_OK;
+}
+
+// ---------------------------------------------------------------- offline file driver -
+// mimo/main.cc:906-918 (read /tmp/rx%d.dat) and :1413-1419 (rx_sig%d.dat, rx_data%d.dat sinks)
+namespace {
+struct FileSet {
+  std::vector<FILE *> f;
+  ~FileSet() { for (FILE *p : f) if (p) fclose(p); }
+  bool open(const char *const *paths, uint32_t n, const char *mode) {
+    f.assign(n, nullptr);
+    if (!paths) return true;
+    for (uint32_t i = 0; i < n; i++) {
+      f[i] = fopen(paths[i], mode);
+      if (!f[i]) { set_error("cannot open %s", paths[i]); return false; }
+    }
+    return true;
+  }
+  bool any() const { for (FILE *p : f) if (p) return true; return false; }
+};
+struct Slot {  // one pinned staging slot
+  unsigned char *base = nullptr;
+  cf *iq = nullptr; uint8_t *tx = nullptr; cf *eq = nullptr; float *llr = nullptr; uint8_t *bits = nullptr, *rxd = nullptr;
+  uint32_t frames = 0;  // complete frames the reader found
+};
+}  // namespace
+
+extern "C" rub_status rub_rx_process_files(rub_rx *h, const rub_file_job *job, uint64_t *frames_done) {
+  if (frames_done) *frames_done = 0;
+  if (!h || !job || job->struct_size != sizeof(rub_file_job) || !job->rx_paths) {
+    set_error("process_files: bad job");
+    return RUB_ERR_INVALID_ARG;
+  }
+  const HostCfg &c = h->h;
+  const uint64_t row = (uint64_t)(c.T + c.D) * c.L;
+  const uint64_t fstride = job->frame_stride ? job->frame_stride : row;
+  if (fstride < row) { set_error("process_files: frame_stride shorter than a frame"); return RUB_ERR_INVALID_ARG; }
+  FileSet rx, txf, eqf, rdf, misc;
+  if (!rx.open(job->rx_paths, c.N, "rb") || !txf.open(job->tx_data_paths, c.N, "rb") ||
+      !eqf.open(job->eq_paths, c.N, "wb") || !rdf.open(job->rx_data_paths, c.N, "wb"))
+    return RUB_ERR_IO;
+  const char *mp[2] = {job->llr_path, job->bits_path};
+  misc.f.assign(2, nullptr);
+  for (int i = 0; i < 2; i++)
+    if (mp[i] && !(misc.f[i] = fopen(mp[i], "wb"))) { set_error("cannot open %s", mp[i]); return RUB_ERR_IO; }
+  const bool want_tx = txf.any(), want_eq = eqf.any(), want_rd = rdf.any(), want_llr = misc.f[0], want_bits = misc.f[1];
+  const size_t pts = (size_t)c.D * c.Mo;  // symbols per (frame, stream)
+  const size_t in_b = (size_t)c.N * row * sizeof(cf), tx_b = c.N * pts, eq_b = c.N * pts * sizeof(cf),
+               llr_b = c.N * pts * c.q * sizeof(float), bits_b = (size_t)c.N * c.D * c.row_bytes, rd_b = c.N * pts;
+  uint32_t chunk = job->chunk_frames ? job->chunk_frames : (uint32_t)std::max<size_t>(1, ((size_t)64 << 20) / in_b);
+  chunk = std::min<uint32_t>(chunk, std::max<uint32_t>(1, job->n_frames));
+  auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t slot_b = al(in_b * chunk) + al(tx_b * chunk) + al(eq_b * chunk) + al(llr_b * chunk) + al(bits_b * chunk) + al(rd_b * chunk);
+  CUDA_TRY(cudaSetDevice(h->device));
+  Slot sl[2];
+  unsigned char *pinned = nullptr;
+  CUDA_TRY(cudaHostAlloc((void **)&pinned, 2 * slot_b, cudaHostAllocDefault));
+  for (int i = 0; i < 2; i++) {
+    unsigned char *p = pinned + (size_t)i * slot_b;
+    sl[i].base = p;
+    sl[i].iq = (cf *)p; p += al(in_b * chunk);
+    sl[i].tx = p; p += al(tx_b * chunk);
+    sl[i].eq = (cf *)p; p += al(eq_b * chunk);
+    sl[i].llr = (float *)p; p += al(llr_b * chunk);
+    sl[i].bits = p; p += al(bits_b * chunk);
+    sl[i].rxd = p;
+  }
+  for (uint32_t r = 0; r < c.N; r++)
+    if (job->first_sample && fseeko(rx.f[r], (off_t)(job->first_sample * sizeof(cf)), SEEK_SET)) {
+      cudaFreeHost(pinned);
+      set_error("process_files: cannot seek %s", job->rx_paths[r]);
+      return RUB_ERR_IO;
+    }
+  // reader: frames [f0, f0+nf) of every antenna file -> slot (dense [frame][rx][row]); stops at a short read
+  std::vector<uint32_t> tmp32(pts);
+  auto read_chunk = [&](Slot &s, uint32_t nf) {
+    s.frames = 0;
+    for (uint32_t f = 0; f < nf; f++) {
+      bool ok = true;
+      for (uint32_t r = 0; r < c.N && ok; r++) {
+        ok = fread(s.iq + ((size_t)f * c.N + r) * row, sizeof(cf), row, rx.f[r]) == row;
+        if (ok && fstride > row) ok = fseeko(rx.f[r], (off_t)((fstride - row) * sizeof(cf)), SEEK_CUR) == 0;
+      }
+      for (uint32_t r = 0; r < c.N && ok && want_tx; r++) {
+        ok = txf.f[r] && fread(tmp32.data(), sizeof(uint32_t), pts, txf.f[r]) == pts;
+        uint8_t *d = s.tx + ((size_t)f * c.N + r) * pts;
+        for (size_t i = 0; ok && i < pts; i++) d[i] = (uint8_t)tmp32[i];
+      }
+      if (!ok) break;
+      s.frames++;
+    }
+  };
+  rub_status st = RUB_OK;
+  uint64_t done = 0;
+  uint32_t issued = std::min(chunk, job->n_frames);
+  read_chunk(sl[0], issued);
+  std::vector<uint32_t> out32(pts);
+  for (int cur = 0; st == RUB_OK && sl[cur].frames > 0; cur ^= 1) {
+    Slot &s = sl[cur];
+    // prefetch the next chunk from disk while this one is on the GPU
+    const bool more = s.frames == std::min(chunk, job->n_frames - (uint32_t)done) && done + s.frames < job->n_frames;
+    const uint32_t next_n = more ? std::min<uint32_t>(chunk, job->n_frames - (uint32_t)(done + s.frames)) : 0;
+    sl[cur ^ 1].frames = 0;
+    std::thread reader;
+    if (next_n) reader = std::thread(read_chunk, std::ref(sl[cur ^ 1]), next_n);
+    rub_rx_io io;
+    memset(&io, 0, sizeof(io));
+    io.iq = (const float *)s.iq;
+    io.tx_data = want_tx ? s.tx : nullptr;
+    if (want_eq) { io.eq = (float *)s.eq; io.out_mask |= RUB_OUT_EQ; }
+    if (want_llr) { io.llr = s.llr; io.out_mask |= RUB_OUT_LLR; }
+    if (want_bits) { io.bits = s.bits; io.out_mask |= RUB_OUT_BITS; }
+    if (want_rd) { io.rx_data = s.rxd; io.out_mask |= RUB_OUT_RXDATA; }
+    st = rub_rx_process_batch_host(h, &io, s.frames);
+    if (st == RUB_OK) {
+      bool ok = true;
+      for (uint32_t f = 0; f < s.frames && ok; f++)
+        for (uint32_t r = 0; r < c.N && ok; r++) {
+          const size_t o = ((size_t)f * c.N + r) * pts;
+          if (eqf.f[r]) ok = fwrite(s.eq + o, sizeof(cf), pts, eqf.f[r]) == pts;
+          if (ok && rdf.f[r]) {
+            for (size_t i = 0; i < pts; i++) out32[i] = s.rxd[o + i];
+            ok = fwrite(out32.data(), sizeof(uint32_t), pts, rdf.f[r]) == pts;
+          }
+        }
+      if (ok && want_llr) ok = fwrite(s.llr, 1, llr_b * s.frames, misc.f[0]) == llr_b * s.frames;
+      if (ok && want_bits) ok = fwrite(s.bits, 1, bits_b * s.frames, misc.f[1]) == bits_b * s.frames;
+      if (!ok) { set_error("process_files: short write"); st = RUB_ERR_IO; }
+      else done += s.frames;
+    }
+    if (reader.joinable()) reader.join();
+  }
+  cudaFreeHost(pinned);
+  if (frames_done) *frames_done = done;
   return st;
 }
