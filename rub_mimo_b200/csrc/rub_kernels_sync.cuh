@@ -48,16 +48,18 @@ __global__ void __launch_bounds__(256) k_sc_metric(const cf *__restrict__ x, uns
 }
 
 // Timing search: blockIdx.y = rx * (nac*N + 1) + code slot (slot 0 = S0, slot a+1 = access code
-// a = code*N + tx); thread = candidate offset i in [0, L).  corr(i) = |sum_n w[base+i+n] *
-// conj(tpl[n])|^2; the first maximum wins (strict '>' in ascending i, framing.cc:717, :736).
+// a = code*N + tx); blockIdx.x = tile of 256 candidate offsets, thread = one offset i in [0, L).
+// corr(i) = |sum_n w[base+i+n] * conj(tpl[n])|^2 with the template and the M+256 window samples
+// of the tile staged in shared memory.  The winner of (rx, slot) is kept as a 64-bit key
+// (corr bits << 32 | ~i) under atomicMax: the largest correlation wins and, among equals, the
+// smallest offset — the reference's strict '>' scan in ascending i (framing.cc:717, :736).
+// Key 0 (nothing above 0) leaves the reference's initial index 0.
 __global__ void __launch_bounds__(256) k_timing_search(const cf *__restrict__ window, unsigned long long wlen,
                                                        const cf *__restrict__ s1, const cf *__restrict__ s0, int M,
-                                                       int L, int N, int nac, int *__restrict__ corr_indices,
-                                                       int *__restrict__ s0_index) {
+                                                       int L, int N, int nac, unsigned long long *__restrict__ keys) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
-  cf *tpl = reinterpret_cast<cf *>(sm_raw);
-  __shared__ float best_v[256];
-  __shared__ int best_i[256];
+  cf *tpl = reinterpret_cast<cf *>(sm_raw);  // [M]
+  cf *xs = tpl + M;                          // [M + 256]
   const int max_ac = nac * N, slots = max_ac + 1;
   const int r = blockIdx.y / slots, slot = blockIdx.y % slots;
   const cf *t = nullptr;
@@ -69,41 +71,26 @@ __global__ void __launch_bounds__(256) k_timing_search(const cf *__restrict__ wi
     base = (long long)L * (ac + 1);
   }
   if (slot == 0 && !s0) return;
-  for (int i = threadIdx.x; i < M; i += blockDim.x) tpl[i] = t[i];
+  const int i0 = blockIdx.x * 256;
+  const cf *w = window + (size_t)r * wlen + base + i0;
+  const long long avail = (long long)wlen - base - i0;  // samples of this row from w on
+  for (int i = threadIdx.x; i < M; i += 256) tpl[i] = t[i];
+  for (int i = threadIdx.x; i < M + 256; i += 256) xs[i] = i < avail ? w[i] : mk(0.f, 0.f);
   __syncthreads();
-  const cf *w = window + (size_t)r * wlen + base;
-  float bv = -1.f;
-  int bi = 0;
-  for (int i = threadIdx.x; i < L; i += blockDim.x) {
-    float ax = 0.f, ay = 0.f;
-    const cf *p = w + i;
-    for (int n = 0; n < M; n++) {
-      const cf xv = p[n], tv = tpl[n];  // x * conj(t)
-      ax = fmaf(xv.x, tv.x, ax); ax = fmaf(xv.y, tv.y, ax);
-      ay = fmaf(xv.y, tv.x, ay); ay = fmaf(-xv.x, tv.y, ay);
-    }
-    const float v = ax * ax + ay * ay;
-    if (v > bv) { bv = v; bi = i; }  // ascending i per thread: first maximum
+  const int i = i0 + threadIdx.x;
+  if (i >= L) return;
+  float ax = 0.f, ay = 0.f;
+  const cf *p = xs + threadIdx.x;
+#pragma unroll 4
+  for (int n = 0; n < M; n++) {
+    const cf xv = p[n], tv = tpl[n];  // x * conj(t)
+    ax = fmaf(xv.x, tv.x, ax); ax = fmaf(xv.y, tv.y, ax);
+    ay = fmaf(xv.y, tv.x, ay); ay = fmaf(-xv.x, tv.y, ay);
   }
-  best_v[threadIdx.x] = bv;
-  best_i[threadIdx.x] = bi;
-  __syncthreads();
-  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
-    if (threadIdx.x < s) {
-      const float ov = best_v[threadIdx.x + s];
-      const int oi = best_i[threadIdx.x + s];
-      if (ov > best_v[threadIdx.x] || (ov == best_v[threadIdx.x] && oi < best_i[threadIdx.x])) {
-        best_v[threadIdx.x] = ov;
-        best_i[threadIdx.x] = oi;
-      }
-    }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    // the reference starts from max = 0 and index 0 and only moves on a strictly larger value
-    const int idx = best_v[0] > 0.f ? best_i[0] : 0;
-    if (slot == 0) s0_index[r] = idx;
-    else corr_indices[r * max_ac + slot - 1] = (int)(base + idx) * (best_v[0] > 0.f ? 1 : 0);
+  const float v = ax * ax + ay * ay;
+  if (v > 0.f) {
+    const unsigned long long key = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);
+    atomicMax(keys + blockIdx.y, key);
   }
 }
 

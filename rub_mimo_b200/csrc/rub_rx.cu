@@ -74,6 +74,8 @@ struct rub_rx {
   float *d_sgn = nullptr;
   cf *d_s1 = nullptr;  // time-domain access codes [tx][code][n] (timing search)
   cf *d_s0 = nullptr;  // time-domain S0 (optional)
+  void *d_sync = nullptr;  // grow-only scratch of the synchronisation calls
+  size_t sync_bytes = 0;
   unsigned char *d_null = nullptr;
   DemapLut lut;
   WeightMode wm;
@@ -266,7 +268,7 @@ extern "C" void rub_rx_destroy(rub_rx *h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
-  cudaFree(h->d_tw); cudaFree(h->d_occ); cudaFree(h->d_sgn); cudaFree(h->d_null); cudaFree(h->d_s1); cudaFree(h->d_s0);
+  cudaFree(h->d_tw); cudaFree(h->d_occ); cudaFree(h->d_sgn); cudaFree(h->d_null); cudaFree(h->d_s1); cudaFree(h->d_s0); cudaFree(h->d_sync);
   cudaFree(h->d_scratch); cudaFree(h->d_fW); cudaFree(h->d_fG); cudaFree(h->d_counters); cudaFree(h->d_pipe);
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);
   for (auto &e : h->pev) if (e) cudaEventDestroy(e);
@@ -675,6 +677,20 @@ extern "C" rub_status rub_comm_destroy(rub_rx *h) {
 }
 
 // ---------------------------------------------------------------- synchronisation -----
+// grow-only device scratch shared by the synchronisation calls (they are synchronous)
+static rub_status sync_scratch(rub_rx *h, size_t bytes, void **out) {
+  if (bytes > h->sync_bytes) {
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_sync);
+    h->d_sync = nullptr;
+    h->sync_bytes = 0;
+    const size_t want = std::max(bytes, (size_t)1 << 20);
+    if (cudaMalloc(&h->d_sync, want) != cudaSuccess) { set_error("out of device memory (%zu B of sync scratch)", want); return RUB_ERR_NOMEM; }
+    h->sync_bytes = want;
+  }
+  *out = h->d_sync;
+  return RUB_OK;
+}
 extern "C" rub_status rub_rx_set_S0(rub_rx *h, const float *s0) {
   if (!h || !s0) return RUB_ERR_INVALID_ARG;
   CUDA_TRY(cudaSetDevice(h->device));
@@ -688,11 +704,12 @@ extern "C" rub_status rub_rx_sc_metric(rub_rx *h, const float *x, uint64_t n, fl
   if (!h || !x || !y) { set_error("sc_metric: NULL argument"); return RUB_ERR_INVALID_ARG; }
   if (n == 0) return RUB_OK;
   CUDA_TRY(cudaSetDevice(h->device));
-  cf *dx = nullptr;
-  float *dy = nullptr;
-  CUDA_TRY(cudaMalloc(&dx, sizeof(cf) * n));
-  if (cudaMalloc(&dy, sizeof(float) * n) != cudaSuccess) { cudaFree(dx); set_error("sc_metric: out of device memory"); return RUB_ERR_NOMEM; }
-  rub_status st = RUB_OK;
+  void *scr = nullptr;
+  const size_t xb = (sizeof(cf) * n + 255) & ~(size_t)255;
+  rub_status st = sync_scratch(h, xb + sizeof(float) * n, &scr);
+  if (st) return st;
+  cf *dx = reinterpret_cast<cf *>(scr);
+  float *dy = reinterpret_cast<float *>((unsigned char *)scr + xb);
   const int M = (int)h->h.M;
   const size_t smem = (size_t)(M + M / 2 + 256) * sizeof(cf);
   cudaError_t e = cudaFuncSetAttribute(k_sc_metric, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -705,8 +722,6 @@ extern "C" rub_status rub_rx_sc_metric(rub_rx *h, const float *x, uint64_t n, fl
   if (e == cudaSuccess) e = cudaMemcpyAsync(y, dy, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
   if (e != cudaSuccess) { set_error("sc_metric: %s", cudaGetErrorString(e)); st = RUB_ERR_CUDA; }
-  cudaFree(dx);
-  cudaFree(dy);
   return st;
 }
 
@@ -720,30 +735,38 @@ extern "C" rub_status rub_rx_timing_search(rub_rx *h, const float *window, uint6
   if (wlen < (uint64_t)c.L * (max_ac + 1) + c.M) { set_error("timing_search: window shorter than the preamble"); return RUB_ERR_INVALID_ARG; }
   if (s0_corr_index && !h->d_s0) { set_error("timing_search: S0 index requested but rub_rx_set_S0 not called"); return RUB_ERR_INVALID_ARG; }
   CUDA_TRY(cudaSetDevice(h->device));
-  cf *dw = nullptr;
-  int *di = nullptr;
-  CUDA_TRY(cudaMalloc(&dw, sizeof(cf) * wlen * c.N));
-  if (cudaMalloc(&di, sizeof(int) * (size_t)c.N * (max_ac + 1)) != cudaSuccess) { cudaFree(dw); set_error("timing_search: out of device memory"); return RUB_ERR_NOMEM; }
-  rub_status st = RUB_OK;
-  const size_t smem = (size_t)c.M * sizeof(cf);
+  void *scr = nullptr;
+  const size_t wb = (sizeof(cf) * wlen * c.N + 255) & ~(size_t)255;
+  const uint32_t nkeys = c.N * (max_ac + 1);
+  rub_status st = sync_scratch(h, wb + sizeof(unsigned long long) * nkeys, &scr);
+  if (st) return st;
+  cf *dw = reinterpret_cast<cf *>(scr);
+  unsigned long long *dk = reinterpret_cast<unsigned long long *>((unsigned char *)scr + wb);
+  std::vector<unsigned long long> keys(nkeys);
+  const size_t smem = (size_t)(2 * c.M + 256) * sizeof(cf);
   cudaError_t e = cudaFuncSetAttribute(k_timing_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e == cudaSuccess) e = cudaMemcpyAsync(dw, window, sizeof(cf) * wlen * c.N, cudaMemcpyHostToDevice, h->stream);
-  if (e == cudaSuccess) e = cudaMemsetAsync(di, 0, sizeof(int) * (size_t)c.N * (max_ac + 1), h->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(dk, 0, sizeof(unsigned long long) * nkeys, h->stream);
   if (e == cudaSuccess) {
-    dim3 grid(1, c.N * (max_ac + 1));
+    dim3 grid((c.L + 255) / 256, nkeys);
     k_timing_search<<<grid, 256, smem, h->stream>>>(dw, wlen, h->d_s1, s0_corr_index ? h->d_s0 : nullptr, (int)c.M,
-                                                    (int)c.L, (int)c.N, (int)c.nac, di, di + (size_t)c.N * max_ac);
+                                                    (int)c.L, (int)c.N, (int)c.nac, dk);
     h->launches += 1;
     e = cudaGetLastError();
   }
-  if (e == cudaSuccess) e = cudaMemcpyAsync(corr_indices, di, sizeof(int) * (size_t)c.N * max_ac, cudaMemcpyDeviceToHost, h->stream);
-  if (e == cudaSuccess && s0_corr_index)
-    e = cudaMemcpyAsync(s0_corr_index, di + (size_t)c.N * max_ac, sizeof(int) * c.N, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(keys.data(), dk, sizeof(unsigned long long) * nkeys, cudaMemcpyDeviceToHost, h->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-  if (e != cudaSuccess) { set_error("timing_search: %s", cudaGetErrorString(e)); st = RUB_ERR_CUDA; }
-  cudaFree(dw);
-  cudaFree(di);
-  return st;
+  if (e != cudaSuccess) { set_error("timing_search: %s", cudaGetErrorString(e)); return RUB_ERR_CUDA; }
+  // decode the winners: index 0 when no correlation rose above the reference's initial max = 0
+  for (uint32_t r = 0; r < c.N; r++)
+    for (uint32_t slot = 0; slot <= max_ac; slot++) {
+      const unsigned long long k = keys[r * (max_ac + 1) + slot];
+      const bool hit = (k >> 32) != 0;
+      const uint32_t i = hit ? 0xffffffffu - (uint32_t)(k & 0xffffffffu) : 0u;
+      if (slot == 0) { if (s0_corr_index) s0_corr_index[r] = (int32_t)i; }
+      else corr_indices[r * max_ac + slot - 1] = hit ? (int32_t)(c.L * slot + i) : 0;
+    }
+  return RUB_OK;
 }
 
 // ---------------------------------------------------------------- transmit side -------
