@@ -151,6 +151,8 @@ struct FusedTraits {
                                                   // block are served by one warp (Y is read once)
   static constexpr int KSTEP = 64 * NWARPS;       // carrier distance between a warp's blocks
   static constexpr int BUF_ELEMS = N * PAD;
+  // small CTAs share an SM: cap their registers so that 512 threads fit (4 x 128 threads x 128 registers)
+  static constexpr int MIN_CTAS = THREADS <= 128 ? 4 : 1;
   static_assert(NT % 32 == 0, "fused path needs NT to be whole warps");
   static_assert(KPW >= 1 && KPW * N * NWARPS == TASKS && (TPW % 2) == 0, "task split");
   static size_t smem_bytes(int q) {
@@ -359,7 +361,7 @@ __device__ __forceinline__ void detect_symbol(const FusedArgs &fa, TaskRegs<N> &
 }
 
 template <int LOG2M, int N>
-__global__ void __launch_bounds__(FusedTraits<LOG2M, N>::THREADS) k_rx_fused(FusedArgs fa, DemapLut lutp) {
+__global__ void __launch_bounds__(FusedTraits<LOG2M, N>::THREADS, FusedTraits<LOG2M, N>::MIN_CTAS) k_rx_fused(FusedArgs fa, DemapLut lutp) {
   using TR = FusedTraits<LOG2M, N>;
   using FF = Fft<LOG2M>;
   using PL = FftPlan<LOG2M>;
