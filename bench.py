@@ -93,6 +93,26 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def _bind_to_gpu_cpus(dev_index):
+    """sched_setaffinity to the CPUs local to CUDA device `dev_index`; returns the previous mask (or None)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[dev_index]) if vis and vis.split(",")[dev_index].isdigit() else dev_index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = (max(os.sched_getaffinity(0)) + 64) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        old = os.sched_getaffinity(0)
+        cpus = {i * 64 + b for i, w in enumerate(mask) for b in range(64) if (w >> b) & 1} & old
+        if cpus and cpus != old:
+            os.sched_setaffinity(0, cpus)
+            return old
+    except Exception:
+        pass
+    return None
+
+
 def metric_values(cfg, frames, seconds):
     samples = frames * cfg.D * cfg.N * (cfg.M + cfg.cp_len)
     det = frames * cfg.D * cfg.Mo
@@ -248,6 +268,9 @@ def run_ours(args):
     # ---- e2e: host buffers through the C-ABI host entry point (H2D + D2H inside) ----
     e2e = None
     if not args.no_e2e:
+        # the pinned staging pages should live on the GPU's own NUMA node: bind this process to the
+        # CPUs NVML reports as local to the GPU while they are allocated and used
+        old_aff = _bind_to_gpu_cpus(torch.cuda.current_device())
         h_iq = torch.from_numpy(iq_u).repeat(reps, 1, 1)[:F].contiguous().pin_memory()
         h_tx = torch.from_numpy(tx_u).repeat(reps, 1, 1, 1)[:F].contiguous().pin_memory()
         h_out = rx.alloc_outputs_host(F, out_mask, pinned=True)
@@ -272,8 +295,11 @@ def run_ours(args):
         d2h = sum(v.nbytes for k, v in h_out.items() if not k.startswith("_")) + cnt.nbytes
         e2e = {"value": e_msps, "unit": "Msamples/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3, "steps": e2e_steps,
-               "note": "rub_rx_process_batch_host, pinned host buffers, 3-stream chunk pipeline"}
+               "note": "rub_rx_process_batch_host, pinned host buffers (allocated on the GPU's NUMA node), "
+                       "3-stream chunk pipeline"}
         del h_iq, h_tx, h_out
+        if old_aff:
+            os.sched_setaffinity(0, old_aff)
 
     clocks = sampler.stop() if rank == 0 else None   # covers the timed loop, the kernel loop and e2e
     cpu = None
