@@ -343,6 +343,31 @@ typedef struct rub_file_job {
  * not an error, the run stops at the last complete frame.                                    */
 rub_status rub_rx_process_files(rub_rx *h, const rub_file_job *job, uint64_t *frames_done);
 
+/* ------------------------------------------- configuration front-end (row f4) ------ */
+/* The fields of the reference's `options` struct (mimo/main.cc:129-156) that are not part of
+ * rub_config: the offline path carries them so that a command line / GUI record written for the
+ * reference parses unchanged.                                                               */
+typedef struct rub_frontend_options {
+  double cent_freq, samp_rate, txgain, rxgain;
+  float dsp_gain;                 /* BASEBAND_GAIN, applied by the transmit side              */
+  char rx_addr[64], tx_addr[64], rx_subdev[32], tx_subdev[32];
+  int32_t verbose;                /* 1 after -v/--verbose, 0 after -q/--quite                 */
+  int32_t help;                   /* 1 after -h/--help                                        */
+  uint32_t num_nullcarriers;      /* GUI record only ("Number of Nullcarriers")               */
+} rub_frontend_options;
+/* read_options (mimo/main.cc:174-240): the same flag names — --freq/-f, --rate/-r, --dsp_gain,
+ * --tx_gain, --rx_gain, --num_subcarriers, --cp_len, --rx_addr, --tx_addr, --tx_subdev,
+ * --rx_subdev, --verbose/-v, --quite/-q, --help/-h — as "--flag value" or "--flag=value".
+ * cfg and fe must be initialised by the caller (defaults); only the given flags are changed.
+ * An unknown flag or a missing / malformed value is RUB_ERR_INVALID_ARG (boost throws).     */
+rub_status rub_config_from_args(int argc, const char *const *argv, rub_config *cfg,
+                                rub_frontend_options *fe);
+/* One device record of the GUI's JSON configuration (Interface/usrp_device.cpp:13-29, keys
+ * "Number of Subcarriers", "Number of Nullcarriers", "Prefix Length", "Training Sequences",
+ * "TX Gain", "RX Gain", "Center Freq.", "Samp. Rate", "Adress", "Subdevice Specifications").
+ * Flat object only; keys that are absent leave cfg / fe unchanged.                          */
+rub_status rub_config_from_json(const char *json, rub_config *cfg, rub_frontend_options *fe);
+
 /* ------------------------------------------------------------- misc ---------------- */
 const char *rub_strerror(rub_status s);
 const char *rub_last_error(void); /* thread-local detail string of the last failure     */

@@ -61,6 +61,32 @@ class rub_msequence(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("m", "g", "a", "n", "v", "b")]
 
 
+class rub_frontend_options(C.Structure):
+    _fields_ = [("cent_freq", C.c_double), ("samp_rate", C.c_double), ("txgain", C.c_double), ("rxgain", C.c_double),
+                ("dsp_gain", C.c_float), ("rx_addr", C.c_char * 64), ("tx_addr", C.c_char * 64),
+                ("rx_subdev", C.c_char * 32), ("tx_subdev", C.c_char * 32), ("verbose", C.c_int32),
+                ("help", C.c_int32), ("num_nullcarriers", C.c_uint32)]
+
+
+def config_from_args(argv, cfg=None, fe=None):
+    """read_options (mimo/main.cc:174-240) over the C ABI: returns (Config, rub_frontend_options)."""
+    cfg = cfg or Config()
+    fe = fe or rub_frontend_options(dsp_gain=0.25)
+    arr = (C.c_char_p * len(argv))(*[a.encode() for a in argv])
+    c = cfg.c
+    _check(lib().rub_config_from_args(len(argv), arr, C.byref(c), C.byref(fe)))
+    return cfg.replace(M=c.M, cp_len=c.cp_len), fe
+
+
+def config_from_json(text, cfg=None, fe=None):
+    """One GUI device record (Interface/usrp_device.cpp:13-29) -> (Config, rub_frontend_options)."""
+    cfg = cfg or Config()
+    fe = fe or rub_frontend_options(dsp_gain=0.25)
+    c = cfg.c
+    _check(lib().rub_config_from_json(text.encode(), C.byref(c), C.byref(fe)))
+    return cfg.replace(M=c.M, cp_len=c.cp_len, num_access_codes=c.num_access_codes), fe
+
+
 class rub_file_job(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("n_frames", C.c_uint32), ("first_sample", C.c_uint64),
                 ("frame_stride", C.c_uint64), ("rx_paths", C.POINTER(C.c_char_p)),
@@ -82,7 +108,8 @@ ABI_SYMBOLS = [
     "rub_rx_sync", "rub_rx_set_path", "rub_rx_get_path", "rub_rx_reset_counters",
     "rub_rx_device_counters", "rub_rx_read_counters", "rub_rx_launch_count", "rub_rx_last_timing",
     "rub_rx_algorithmic_bytes", "rub_rx_sc_metric", "rub_rx_timing_search", "rub_rx_set_S0",
-    "rub_framegen_batch_device", "rub_rx_process_files", "rub_comm_get_unique_id", "rub_comm_init", "rub_allreduce_counters",
+    "rub_framegen_batch_device", "rub_rx_process_files", "rub_config_from_args", "rub_config_from_json",
+    "rub_comm_get_unique_id", "rub_comm_init", "rub_allreduce_counters",
     "rub_comm_destroy", "rub_shard_range", "rub_msequence_init", "rub_msequence_reset",
     "rub_msequence_advance", "rub_msequence_generate_symbol", "rub_ofdmframe_init_default_sctype",
     "rub_ofdmframe_validate_sctype", "rub_ofdmframe_init_S0", "rub_ofdmframe_init_S1",
@@ -189,6 +216,16 @@ class Config:
     def with_noise_var(self, nv):
         return Config(self.M, self.cp_len, self.N, self.nac, self.D, self.q, self.detector,
                       self.estimator, self.P, self.flags, nv, self.sctype)
+
+    def replace(self, **kw):
+        """A copy with some constructor arguments changed (the allocation is dropped when M changes)."""
+        cur = dict(M=self.M, cp_len=self.cp_len, num_streams=self.N, num_access_codes=self.nac,
+                   num_data_symbols=self.D, modulation=self.q, detector=self.detector, estimator=self.estimator,
+                   pilot_spacing=self.P, flags=self.flags, noise_var=self.noise_var, sctype=self.sctype)
+        if kw.get("M", self.M) != self.M and "sctype" not in kw:
+            cur["sctype"] = None
+        cur.update(kw)
+        return Config(**cur)
 
     def validate(self):
         _check(lib().rub_config_validate(C.byref(self.c)))

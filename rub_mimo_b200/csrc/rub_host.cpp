@@ -600,4 +600,111 @@ rub_status rub_file_write_u32(const char *path, const uint32_t *src, uint64_t n)
   return w == n ? RUB_OK : RUB_ERR_IO;
 }
 
+
+// ------------------------------------------------------------- configuration front-end
+// read_options, mimo/main.cc:174-240
+static bool parse_double(const char *v, double *out) {
+  if (!v || !*v) return false;
+  char *end = nullptr;
+  const double d = strtod(v, &end);
+  if (end == v || *end) return false;
+  *out = d;
+  return true;
+}
+static bool parse_uint(const char *v, uint32_t *out) {
+  if (!v || !*v || *v == '-') return false;
+  char *end = nullptr;
+  const unsigned long u = strtoul(v, &end, 10);
+  if (end == v || *end || u > 0xfffffffful) return false;
+  *out = (uint32_t)u;
+  return true;
+}
+static void copy_str(char *dst, size_t cap, const char *src) {
+  const size_t n = std::min(strlen(src), cap - 1);
+  memcpy(dst, src, n);
+  dst[n] = 0;
+}
+
+rub_status rub_config_from_args(int argc, const char *const *argv, rub_config *cfg, rub_frontend_options *fe) {
+  if (!cfg || !fe || (argc > 0 && !argv)) { set_error("config_from_args: NULL argument"); return RUB_ERR_INVALID_ARG; }
+  for (int i = 1; i < argc; i++) {
+    std::string a = argv[i] ? argv[i] : "";
+    std::string val;
+    bool has_val = false;
+    const size_t eq = a.find('=');
+    if (a.rfind("--", 0) == 0 && eq != std::string::npos) { val = a.substr(eq + 1); a = a.substr(0, eq); has_val = true; }
+    if (a == "-h" || a == "--help") { fe->help = 1; continue; }
+    if (a == "-v" || a == "--verbose") { fe->verbose = 1; continue; }
+    if (a == "-q" || a == "--quite") { fe->verbose = 0; continue; }
+    static const char *const valued[] = {"-f", "--freq", "-r", "--rate", "--dsp_gain", "--tx_gain", "--rx_gain",
+                                         "--num_subcarriers", "--cp_len", "--rx_addr", "--tx_addr", "--tx_subdev",
+                                         "--rx_subdev"};
+    bool known = false;
+    for (const char *k : valued) known = known || a == k;
+    if (!known) { set_error("unrecognised option '%s'", a.c_str()); return RUB_ERR_INVALID_ARG; }
+    if (!has_val) {
+      if (i + 1 >= argc || !argv[i + 1]) { set_error("the required argument for option '%s' is missing", a.c_str()); return RUB_ERR_INVALID_ARG; }
+      val = argv[++i];
+    }
+    bool ok = true;
+    double d = 0;
+    if (a == "-f" || a == "--freq") { ok = parse_double(val.c_str(), &d); if (ok) fe->cent_freq = d; }
+    else if (a == "-r" || a == "--rate") { ok = parse_double(val.c_str(), &d); if (ok) fe->samp_rate = d; }
+    else if (a == "--dsp_gain") { ok = parse_double(val.c_str(), &d); if (ok) fe->dsp_gain = (float)d; }
+    else if (a == "--tx_gain") { ok = parse_double(val.c_str(), &d); if (ok) fe->txgain = d; }
+    else if (a == "--rx_gain") { ok = parse_double(val.c_str(), &d); if (ok) fe->rxgain = d; }
+    else if (a == "--num_subcarriers") ok = parse_uint(val.c_str(), &cfg->M);
+    else if (a == "--cp_len") ok = parse_uint(val.c_str(), &cfg->cp_len);
+    else if (a == "--rx_addr") copy_str(fe->rx_addr, sizeof(fe->rx_addr), val.c_str());
+    else if (a == "--tx_addr") copy_str(fe->tx_addr, sizeof(fe->tx_addr), val.c_str());
+    else if (a == "--tx_subdev") copy_str(fe->tx_subdev, sizeof(fe->tx_subdev), val.c_str());
+    else if (a == "--rx_subdev") copy_str(fe->rx_subdev, sizeof(fe->rx_subdev), val.c_str());
+    if (!ok) { set_error("the argument ('%s') for option '%s' is invalid", val.c_str(), a.c_str()); return RUB_ERR_INVALID_ARG; }
+  }
+  return RUB_OK;
+}
+
+// value text of "key" in a flat JSON object: number / string token without the quotes
+static bool json_value(const char *json, const char *key, std::string *out) {
+  const std::string pat = std::string("\"") + key + "\"";
+  const char *p = strstr(json, pat.c_str());
+  if (!p) return false;
+  p += pat.size();
+  while (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r') p++;
+  if (*p != ':') return false;
+  p++;
+  while (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r') p++;
+  out->clear();
+  if (*p == '"') {
+    for (p++; *p && *p != '"'; p++) { if (*p == '\\' && p[1]) p++; out->push_back(*p); }
+    return *p == '"';
+  }
+  while (*p && *p != ',' && *p != '}' && *p != ' ' && *p != '\n' && *p != '\r' && *p != '\t') out->push_back(*p++);
+  return !out->empty();
+}
+
+// Interface/usrp_device.cpp:13-29
+rub_status rub_config_from_json(const char *json, rub_config *cfg, rub_frontend_options *fe) {
+  if (!json || !cfg || !fe) { set_error("config_from_json: NULL argument"); return RUB_ERR_INVALID_ARG; }
+  std::string v;
+  double d;
+  auto num = [&](const char *key, double *dst) -> bool {
+    if (!json_value(json, key, &v)) return true;  // absent: unchanged
+    if (!parse_double(v.c_str(), dst)) { set_error("JSON key \"%s\": '%s' is not a number", key, v.c_str()); return false; }
+    return true;
+  };
+  double M = cfg->M, nn = fe->num_nullcarriers, cp = cfg->cp_len, ts = cfg->num_access_codes;
+  if (!num("Number of Subcarriers", &M) || !num("Number of Nullcarriers", &nn) || !num("Prefix Length", &cp) ||
+      !num("Training Sequences", &ts) || !num("TX Gain", &fe->txgain) || !num("RX Gain", &fe->rxgain) ||
+      !num("Center Freq.", &fe->cent_freq) || !num("Samp. Rate", &fe->samp_rate))
+    return RUB_ERR_INVALID_ARG;
+  for (double x : {M, nn, cp, ts})
+    if (x < 0 || x > 4294967295.0 || x != (double)(uint32_t)x) { set_error("JSON record: %g is not an unsigned integer", x); return RUB_ERR_INVALID_ARG; }
+  cfg->M = (uint32_t)M; fe->num_nullcarriers = (uint32_t)nn; cfg->cp_len = (uint32_t)cp; cfg->num_access_codes = (uint32_t)ts;
+  (void)d;
+  if (json_value(json, "Adress", &v)) { copy_str(fe->rx_addr, sizeof(fe->rx_addr), v.c_str()); copy_str(fe->tx_addr, sizeof(fe->tx_addr), v.c_str()); }
+  if (json_value(json, "Subdevice Specifications", &v)) { copy_str(fe->rx_subdev, sizeof(fe->rx_subdev), v.c_str()); copy_str(fe->tx_subdev, sizeof(fe->tx_subdev), v.c_str()); }
+  return RUB_OK;
+}
+
 }  // extern "C"
