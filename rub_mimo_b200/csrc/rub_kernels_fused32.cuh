@@ -14,7 +14,7 @@
 // Both phases of k_rx_fused are latency bound at 16 warps/SM; this kernel runs
 // them at 32.  Status: bit-exact, but the lane-role selects of the split radix-16 stages and the
 // per-half-task overheads add ~30 % instructions, so at 62 % issue utilisation it is 8 % slower than
-// k_rx_fused on C3 (1.71 vs 1.58 ms).  Opt-in (RUB_FUSED32=1) until it wins.
+// k_rx_fused on C3 (1.71 vs 1.58 ms).  Opt-in (rub_rx_set_path(h, RUB_PATH_FUSED32)) until it wins.
 #pragma once
 #include "rub_kernels_fused.cuh"
 

@@ -279,7 +279,7 @@ extern "C" void rub_rx_destroy(rub_rx *h) {
 }
 
 extern "C" rub_status rub_rx_set_path(rub_rx *h, uint32_t path) {
-  if (!h || path > RUB_PATH_FUSED) return RUB_ERR_INVALID_ARG;
+  if (!h || path > RUB_PATH_FUSED32) return RUB_ERR_INVALID_ARG;
   h->path = path;
   return RUB_OK;
 }
@@ -463,8 +463,15 @@ static rub_status run_staged(rub_rx *h, ChainArgs a, const rub_rx_io *io, uint32
 
 static rub_status run_fused(rub_rx *h, const ChainArgs &a, uint32_t n_frames, bool timed) {
   const HostCfg &c = h->h;
+  const bool want32 = h->path == RUB_PATH_FUSED32;
+  if (h->fused_ready && h->fused32 != want32) {  // the variant changed: shared-memory size and grid are per kernel
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_fW); cudaFree(h->d_fG);
+    h->d_fW = nullptr; h->d_fG = nullptr;
+    h->fused_ready = false;
+  }
   if (!h->fused_ready) {
-    h->fused32 = fused32_has_instance(c.log2M, c.N) && getenv("RUB_FUSED32") != nullptr;
+    h->fused32 = want32;
     int grid = 0;
     size_t smem = 0;
     rub_status st = fused_prepare_dispatch(h, &smem, &grid);
@@ -489,7 +496,7 @@ static rub_status run_fused(rub_rx *h, const ChainArgs &a, uint32_t n_frames, bo
   if (timed) cudaEventRecord(h->ev[3], h->stream);
   h->launches += 1;
   CUDA_TRY(cudaGetLastError());
-  h->last_path = RUB_PATH_FUSED;
+  h->last_path = want32 ? RUB_PATH_FUSED32 : RUB_PATH_FUSED;
   return RUB_OK;
 }
 
@@ -524,11 +531,12 @@ static rub_status process_device(rub_rx *h, const rub_rx_io *io, uint32_t n_fram
     return RUB_ERR_INVALID_ARG;
   }
   const bool can_fuse = fused_eligible(h, io, frame_stride, rx_stride);
-  if (h->path == RUB_PATH_FUSED && !can_fuse) {
+  const bool req_fused = h->path == RUB_PATH_FUSED || h->path == RUB_PATH_FUSED32;
+  if (req_fused && (!can_fuse || (h->path == RUB_PATH_FUSED32 && !fused32_has_instance(h->h.log2M, h->h.N)))) {
     set_error("fused path requested but the configuration / buffers are not eligible");
     return RUB_ERR_UNSUPPORTED;
   }
-  const bool use_fused = (h->path == RUB_PATH_FUSED) || (h->path == RUB_PATH_AUTO && can_fuse);
+  const bool use_fused = req_fused || (h->path == RUB_PATH_AUTO && can_fuse);
   if (timed) cudaEventRecord(h->ev[0], h->stream);
   rub_status st = use_fused ? run_fused(h, a, n_frames, timed) : run_staged(h, a, io, n_frames, timed);
   if (timed) cudaEventRecord(h->ev[1], h->stream);
@@ -901,8 +909,7 @@ extern "C" rub_status rub_rx_process_files(rub_rx *h, const rub_file_job *job, u
   };
   rub_status st = RUB_OK;
   uint64_t done = 0;
-  uint32_t issued = std::min(chunk, job->n_frames);
-  read_chunk(sl[0], issued);
+  read_chunk(sl[0], std::min(chunk, job->n_frames));
   std::vector<uint32_t> out32(pts);
   for (int cur = 0; st == RUB_OK && sl[cur].frames > 0; cur ^= 1) {
     Slot &s = sl[cur];

@@ -62,11 +62,17 @@ def test_fused_path_matches_oracle(name):
 
 
 @pytest.mark.parametrize("name", ["c3_small", "c3_biased_zf"])
-def test_fused32_variant_matches_oracle(name, monkeypatch):
+def test_fused32_variant_matches_oracle(name):
     """The opt-in 32-warp fused kernel (rub_kernels_fused32.cuh, 4x4 / 2048) is bit-exact too."""
-    monkeypatch.setenv("RUB_FUSED32", "1")
-    got = _run(name, rub.PATH_FUSED)
-    assert got["path"] == rub.PATH_FUSED
+    got = _run(name, rub.PATH_FUSED32)
+    assert got["path"] == rub.PATH_FUSED32
+
+
+def test_fused32_is_refused_where_it_has_no_instance():
+    kw, nf, sk = CASES["c2_small"]
+    cfg, S1, iq, tx = make_case(rub.Config(**kw), 2, seed=3, **sk)
+    with pytest.raises(rub.RubError):
+        gpu_run(cfg, S1, iq, tx, path=rub.PATH_FUSED32)
 
 
 def test_ragged_allocation_uses_staged_path():
