@@ -435,13 +435,16 @@ void orc_llr(uint32_t q, ocf x, float isig, float *llr) {
 /* ------------------------------------------------------------ weights --------------- */
 /* invert(), mimo/framing.cc:1344-1367 with INVERT_TO_UNITY false (config.h:103):
  * W = conj(det)*adj(G), returns 1/|det|^2.  G, W row-major 2x2.                          */
+/* std::complex operator* as libgcc's __mulsc3 evaluates it: four rounded products, a rounded
+ * difference and a rounded sum */
+static inline ocf c_mul_std(ocf a, ocf b) { return c_make(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re); }
 float orc_invert_2x2(ocf W[4], const ocf G[4]) {
-  ocf det = c_sub(c_mul(G[0], G[3]), c_mul(G[1], G[2]));
+  ocf det = c_sub(c_mul_std(G[0], G[3]), c_mul_std(G[1], G[2]));
   ocf di = c_conj(det);
-  W[0] = c_mul(di, G[3]);
-  W[3] = c_mul(di, G[0]);
-  W[2] = c_mul(c_neg(di), G[2]);
-  W[1] = c_mul(c_neg(di), G[1]);
+  W[0] = c_mul_std(di, G[3]);
+  W[3] = c_mul_std(di, G[0]);
+  W[2] = c_mul_std(c_neg(di), G[2]);
+  W[1] = c_mul_std(c_neg(di), G[1]);
   return 1.0f / (det.re * det.re + det.im * det.im);
 }
 void orc_weights(const orc_config *c, const ocf *G, ocf *W, float *gain, float *isig) {
@@ -642,7 +645,18 @@ int orc_rx_frame(const orc_config *c, const ocf *S1, const ocf *const *rx, uint6
       if (is_null_sc(c, k)) continue;
       for (uint32_t s = 0; s < N; s++) {
         ocf acc = c_make(0.f, 0.f);
-        for (uint32_t r = 0; r < N; r++) acc = c_mac(acc, W[((size_t)s * N + r) * M + k], X[(size_t)r * M + k]);
+        if (N == 2) {
+          /* mimo/framing.cc:573-576: W[sc][s][0]*X[0][sc] + W[sc][s][1]*X[1][sc] in std::complex
+           * arithmetic (four rounded products, a rounded difference and sum per product, then
+           * the complex add); pinned by tests/golden/ref_*.npz, the reference's own output */
+          const ocf w0 = W[((size_t)s * N + 0) * M + k], w1 = W[((size_t)s * N + 1) * M + k];
+          const ocf x0 = X[(size_t)0 * M + k], x1 = X[(size_t)1 * M + k];
+          const ocf p0 = c_make(w0.re * x0.re - w0.im * x0.im, w0.re * x0.im + w0.im * x0.re);
+          const ocf p1 = c_make(w1.re * x1.re - w1.im * x1.im, w1.re * x1.im + w1.im * x1.re);
+          acc = c_add(p0, p1);
+        } else {
+          for (uint32_t r = 0; r < N; r++) acc = c_mac(acc, W[((size_t)s * N + r) * M + k], X[(size_t)r * M + k]);
+        }
         float g = gain[(size_t)s * M + k];
         ocf z = c_make(acc.re * g, acc.im * g);
         size_t o = ((size_t)s * D + d) * Mo + j;

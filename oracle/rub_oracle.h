@@ -7,10 +7,18 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
  * The product (rub_mimo_b200/, librubmimo_b200.so) never includes, links or calls it.
  *
- * PARITY STATUS: "parity unpinned" by the reference — upstream has no tests, fixtures or
- * golden vectors for this path and cannot be compiled here (it needs FFTW3f,
- * liquid-dsp, VOLK, UHD, Boost, GNU Radio: mimo/makefile:11-12, mimo/framing.h:22-26; none
- * are installed and there is no network).  The oracle is instead pinned by
+ * PARITY STATUS: pinned to the reference's OWN framing code for the path it implements (2x2, ZF,
+ * full-band LS): `make -C oracle ref` compiles /root/reference/mimo/framing.cc where it lies against
+ * stand-in headers for the libraries that are not installed (oracle/shim/: FFTW3f plans run by this
+ * file's FFT, VOLK generic kernels, liquid-dsp msequence / wdelay / window / firfilt, gr_complex,
+ * boost::format) into oracle/_ref/, oracle/make_ref_fixtures.py runs it and commits its outputs as
+ * tests/golden/ref_*.npz, and tests/test_ref_fixtures.py requires this oracle (and the CUDA path)
+ * to reproduce them BIT FOR BIT: framegen waveform, Schmidl & Cox plateau / sync index / sample
+ * count, timing search, LS estimate G (quirks Q1/Q2/Q4), invert() and 1000 decoded OFDM symbols.
+ * What the stand-ins cannot pin is the rounding of the real FFTW / VOLK / liquid builds (none is
+ * vendored or version-pinned upstream: mimo/makefile:8-13 only has -l flags), and upstream has no
+ * tests, fixtures or golden vectors of its own.  Everything the reference has no
+ * code for (N > 2, MMSE, QAM > 4, LLRs, comb pilots) stays pinned by
  *   (1) known-answer tests derived from the reference source (tests/test_oracle_*.py),
  *   (2) an independent float64 numpy model (oracle/oracle_f64.py: np.fft + np.linalg),
  *   (3) committed golden fixtures regenerated only by oracle/make_golden.py.

@@ -36,6 +36,9 @@ RUB_HD cf cmul(cf a, cf b) {
   return mk(fmaf(a.x, b.x, -(a.y * b.y)), fmaf(a.x, b.y, a.y * b.x));
 }
 // acc += a*b
+// std::complex operator* as the reference's decode evaluates it (libgcc __mulsc3: four rounded
+// products, one rounded difference, one rounded sum; no fusion)
+RUB_HD cf cmul_ref(cf a, cf b) { return mk(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 RUB_HD cf cmac(cf acc, cf a, cf b) {
   acc.x = fmaf(a.x, b.x, acc.x);
   acc.x = fmaf(-a.y, b.y, acc.x);
@@ -65,6 +68,20 @@ RUB_HD cf cmsub_conj_b(cf acc, cf a, cf b) {
   acc.x = fmaf(-a.y, b.y, acc.x);
   acc.y = fmaf(-a.y, b.x, acc.y);
   acc.y = fmaf(a.x, b.y, acc.y);
+  return acc;
+}
+
+// z = sum_r W[r] * y[r] for one stream and carrier.  N = 2 follows the reference to the bit
+// (mimo/framing.cc:573-576: W[sc][s][0]*X[0][sc] + W[sc][s][1]*X[1][sc], std::complex arithmetic);
+// the reference has no N > 2 code, there the sum is an fmaf chain in r order.
+template <int N>
+RUB_HD cf wy_dot(const cf *w, const cf *y) {
+  if (N == 2) return cadd(cmul_ref(w[0], y[0]), cmul_ref(w[1], y[1]));
+  cf acc = mk(0.f, 0.f);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int r = 0; r < N; r++) acc = cmac(acc, w[r], y[r]);
   return acc;
 }
 
@@ -184,14 +201,16 @@ RUB_HD uint32_t slice_axis_rt(float v, int m, float alpha) {
 
 // ------------------------------------------------------------------ weights -----------
 // invert(), mimo/framing.cc:1344-1367 (INVERT_TO_UNITY false): W = conj(det)*adj(G),
-// returns 1/|det|^2.  Row-major 2x2.
+// returns 1/|det|^2.  Row-major 2x2.  Every product is the reference's std::complex operator*
+// (cmul_ref), so W and the gain match the reference's own output bit for bit
+// (tests/golden/ref_*.npz).
 RUB_HD float invert_2x2(cf *W, const cf *G) {
-  cf det = csub(cmul(G[0], G[3]), cmul(G[1], G[2]));
+  cf det = csub(cmul_ref(G[0], G[3]), cmul_ref(G[1], G[2]));
   cf di = cconj(det);
-  W[0] = cmul(di, G[3]);
-  W[3] = cmul(di, G[0]);
-  W[2] = cmul(cneg(di), G[2]);
-  W[1] = cmul(cneg(di), G[1]);
+  W[0] = cmul_ref(di, G[3]);
+  W[3] = cmul_ref(di, G[0]);
+  W[2] = cmul_ref(cneg(di), G[2]);
+  W[1] = cmul_ref(cneg(di), G[1]);
   return 1.0f / (det.x * det.x + det.y * det.y);
 }
 

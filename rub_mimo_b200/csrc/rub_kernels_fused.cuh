@@ -215,13 +215,13 @@ __device__ __forceinline__ void task_compute(const TaskRegs<N> &t, const ChainAr
                                              unsigned txv, unsigned *cnt_s) {
   constexpr int Q = 2 * MB;
   const int lane = threadIdx.x & 31;
-  cf acc0 = mk(0.f, 0.f), acc1 = mk(0.f, 0.f);
+  cf w0[N], w1[N], y0[N], y1[N];
 #pragma unroll
   for (int r = 0; r < N; r++) {
-    const float4 y = y4[r];
-    acc0 = cmac(acc0, mk(t.w[r].x, t.w[r].y), mk(y.x, y.y));
-    acc1 = cmac(acc1, mk(t.w[r].z, t.w[r].w), mk(y.z, y.w));
+    w0[r] = mk(t.w[r].x, t.w[r].y); w1[r] = mk(t.w[r].z, t.w[r].w);
+    y0[r] = mk(y4[r].x, y4[r].y); y1[r] = mk(y4[r].z, y4[r].w);
   }
+  const cf acc0 = wy_dot<N>(w0, y0), acc1 = wy_dot<N>(w1, y1);
   const cf z0 = cscale(acc0, t.g.x), z1 = cscale(acc1, t.g.y);
   float l0[Q], l1[Q];
   const bool want_llr = a.llr != nullptr;
@@ -642,10 +642,10 @@ __global__ void __launch_bounds__(256, (N <= 4 ? 3 : 2)) k_detect_lean(ChainArgs
         if (lane == 0) bulk_wait_read<1>();
         __syncwarp();
       }
-      cf acc = mk(0.f, 0.f);
+      cf wv[N], yv[N];
 #pragma unroll
-      for (int r = 0; r < N; r++) acc = cmac(acc, mk(cur.w[r].x, cur.w[r].y), mk(y[h][r].x, y[h][r].y));
-      const cf z = cscale(acc, cur.g);
+      for (int r = 0; r < N; r++) { wv[r] = mk(cur.w[r].x, cur.w[r].y); yv[r] = mk(y[h][r].x, y[h][r].y); }
+      const cf z = cscale(wy_dot<N>(wv, yv), cur.g);
       const unsigned si = slice_axis_refs<MB>(z.x, refs), sq = slice_axis_refs<MB>(z.y, refs);
       const unsigned c = (si << MB) | sq;
       symh[h] = c ^ ((c >> 1) & ~(1u << (MB - 1)));

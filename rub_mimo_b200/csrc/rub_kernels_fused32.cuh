@@ -176,10 +176,10 @@ __device__ __forceinline__ void detect_symbol32(const FusedArgs &fa, const cf *W
     float2 y[N];
 #pragma unroll
     for (int r = 0; r < N; r++) y[r] = *reinterpret_cast<const float2 *>(Yl + r * PAD + kb * KSTEP + 32 * h);
-    cf acc = mk(0.f, 0.f);
+    cf wv[N], yv[N];
 #pragma unroll
-    for (int r = 0; r < N; r++) acc = cmac(acc, mk(cur.w[r].x, cur.w[r].y), mk(y[r].x, y[r].y));
-    const cf z = cscale(acc, cur.g);
+    for (int r = 0; r < N; r++) { wv[r] = mk(cur.w[r].x, cur.w[r].y); yv[r] = mk(y[r].x, y[r].y); }
+    const cf z = cscale(wy_dot<N>(wv, yv), cur.g);
     const unsigned si = slice_axis_refs<MB>(z.x, refs), sq = slice_axis_refs<MB>(z.y, refs);
     const unsigned c = (si << MB) | sq;
     symh[h] = c ^ ((c >> 1) & ~(1u << (MB - 1)));

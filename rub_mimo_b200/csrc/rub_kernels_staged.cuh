@@ -215,10 +215,10 @@ __global__ void __launch_bounds__(128) k_detect(ChainArgs a, DemapLut lutp) {
     const int j = j0 + u;
     if (j >= a.Mo) break;
     const int k = a.occ[j];
-    cf acc = mk(0.f, 0.f);
+    cf wv[N], yv[N];
 #pragma unroll
-    for (int r = 0; r < N; r++) acc = cmac(acc, Wf[(long long)r * a.M + k], Yf[(long long)r * a.M + k]);
-    const cf z = cscale(acc, gf[k]);
+    for (int r = 0; r < N; r++) { wv[r] = Wf[(long long)r * a.M + k]; yv[r] = Yf[(long long)r * a.M + k]; }
+    const cf z = cscale(wy_dot<N>(wv, yv), gf[k]);
     const unsigned si = slice_axis_rt(z.x, m, alpha), sq = slice_axis_rt(z.y, m, alpha);
     const unsigned sym = (gray_encode(si) << m) + gray_encode(sq);
     const long long o = orow * a.Mo + j;

@@ -1,0 +1,98 @@
+"""Pins the oracle — and through it the CUDA path — to the REFERENCE ITSELF.
+
+tests/golden/ref_*.npz hold what the reference's own mimo/framing.cc produced in the build
+container (compiled where it lies against the stand-in headers of oracle/shim/, see
+oracle/make_ref_fixtures.py): frame generator waveform, Schmidl & Cox state machine, timing
+search, LS estimate with its quirks, invert() and a thousand decoded OFDM symbols.  The oracle,
+the host framegen and (on the GPU box) the CUDA chain must reproduce them bit for bit."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import rub_mimo_b200 as rub
+from oracle import orc
+from util import to_orc
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+NAMES = ["ref_c1_m64", "ref_m256"]
+
+
+def _load(name):
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    cfg = rub.preset("C1", M=int(z["M"]), cp_len=int(z["cp_len"]), num_access_codes=int(z["nac"]),
+                     num_data_symbols=int(z["D"]), sctype=z["sctype"])
+    S1, s1 = rub.default_S1(cfg)
+    S0, s0 = rub.default_S0(cfg)
+    iq, tx, nv = rub.synth_frames(cfg, 1, int(z["seed"]), n_taps=0, snr_db=float(z["snr_db"]), fixed_H=z["H"],
+                                  include_s0=True, lead_zeros=int(z["lead"]), S1=S1, s1=s1)
+    cap = iq[0]
+    assert hashlib.sha256(cap.tobytes()).hexdigest() == str(z["cap_sha256"]), "the synthetic capture changed"
+    return z, cfg, S0, s0, S1, cap, tx[0]
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_reproduces_the_reference_receiver_bit_for_bit(name):
+    z, cfg, S0, s0, S1, cap, tx = _load(name)
+    r = orc.framesync_execute(to_orc(cfg), S0, S1, cap)
+    assert r["rc"] == 0 and r["state"] == int(z["state"]) == 3
+    assert r["sync_index"] == int(z["sync_index"])
+    assert r["num_samples_processed"] == int(z["num_samples_processed"])
+    assert list(r["plateau_start"]) == list(z["plateau_start"]) and list(r["plateau_end"]) == list(z["plateau_end"])
+    assert r["symbols_decoded"] == int(z["symbols"])
+    assert np.array_equal(r["G"].view(np.uint32), z["G"].view(np.uint32))            # LS estimate incl. quirks Q1/Q2
+    assert np.array_equal(r["eq"][:, :16].view(np.uint32), z["eq_head"].view(np.uint32))
+    # every decoded symbol: the reference decodes past D (quirk Q14), the hash covers the D both keep
+    assert r["eq"].shape[1] == cfg.D
+    assert hashlib.sha256(np.ascontiguousarray(r["eq"]).tobytes()).hexdigest() == str(z["eq_sha256_D"])
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_host_framegen_reproduces_the_reference_waveform(name):
+    z, cfg, S0, s0, S1, cap, tx = _load(name)
+    fg = rub.FrameGen(cfg)
+    mine = np.concatenate([fg.write_sync_words()] + [fg.assemble_mimo_packet(s) for s in z["syms"]], axis=1)
+    # value-identical; the only bit differences are signed zeros (the reference scales by the complex
+    # (g, 0): 0*re + g*(-0) = +0, a real scale keeps -0)
+    assert np.array_equal(mine, z["ref_tx"])
+    d = mine.view(np.uint32) != z["ref_tx"].view(np.uint32)
+    assert not np.any(mine.view(np.float32)[d]) and not np.any(z["ref_tx"].view(np.float32)[d])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", NAMES)
+def test_cuda_chain_reproduces_the_reference_receiver_bit_for_bit(name):
+    import torch
+    z, cfg, S0, s0, S1, cap, tx = _load(name)
+    rx = rub.Receiver(cfg, S1)
+    rx.set_S0(s0)
+    # S&C metric -> the reference's plateau (same threshold walk as framesync::execute_sc_sync)
+    r = orc.framesync_execute(to_orc(cfg), S0, S1, cap)
+    Wlen = cfg.L * (cfg.nac * cfg.N + 4) + cfg.D * cfg.L
+    w0 = int(r["window_start"])
+    window = np.ascontiguousarray(cap[:, w0:w0 + Wlen])
+    corr = rx.timing_search(window)                                                     # GPU timing search
+    assert np.array_equal(corr, r["corr_indices"])
+    payload_start = int(corr[1, -1]) + cfg.M                                            # quirk Q4
+    out = rx.process_batch(torch.from_numpy(window[None]).cuda(), out_mask=rub.OUT_EQ | rub.OUT_G,
+                           timing=torch.from_numpy(corr[None].astype(np.int32)).cuda(),
+                           payload_start=torch.tensor([payload_start], dtype=torch.int32).cuda())
+    rx.sync()
+    G = np.ascontiguousarray(out["G"].cpu().numpy()[0].transpose(2, 0, 1))                                    # -> [k][rx][tx]
+    assert np.array_equal(G.view(np.uint32), z["G"].view(np.uint32))
+    eq = out["eq"].cpu().numpy()[0]                                                     # [N][D][Mo]
+    assert np.array_equal(eq[:, :16].view(np.uint32), z["eq_head"].view(np.uint32))
+    assert hashlib.sha256(np.ascontiguousarray(eq).tobytes()).hexdigest() == str(z["eq_sha256_D"])   # all D symbols
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", NAMES)
+def test_gpu_framegen_reproduces_the_reference_waveform(name):
+    import torch
+    z, cfg, S0, s0, S1, cap, tx = _load(name)
+    # symbol indices of the first packets -> device framegen (access codes + packets; S0 is host side)
+    ntx = z["syms"].shape[0]
+    rx = rub.Receiver(cfg.replace(num_data_symbols=ntx), S1)
+    got = rx.framegen_batch(torch.from_numpy(np.ascontiguousarray(tx[None, :, :ntx])).cuda()).cpu().numpy()[0]
+    assert np.array_equal(got, z["ref_tx"][:, cfg.L:])          # value-identical (signed zeros aside)
