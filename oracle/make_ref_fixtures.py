@@ -71,6 +71,10 @@ CASES = {
     # name: (M, cp, nac, D = PID_MAX of mimo/config.h, seed, snr_db, flat 2x2 channel)
     "ref_c1_m64": (64, 16, 20, 1000, 0xC1, 30.0, [[1, 0.5], [0.5j, 1]]),
     "ref_m256": (256, 20, 4, 1000, 0xC2, 27.0, [[0.9, -0.3j], [0.2 + 0.4j, 1.1]]),
+    # 3-tap Rayleigh links: the access codes of different links peak at different offsets (quirk Q2)
+    "ref_m512_multipath": (512, 36, 8, 1000, 0xC5, 28.0, None),
+    # the reference's default geometry (mimo/config.h:65-66, :94): 2048 carriers, cp 152, 20 access codes
+    "ref_m2048_default": (2048, 152, 20, 1000, 0xC6, 30.0, [[1, 0.5], [0.5j, 1]]),
 }
 
 
@@ -82,12 +86,12 @@ def run_case(name):
     S1, s1 = rub.default_S1(cfg)
     S0, s0 = rub.default_S0(cfg)
     lead = (nac * 2 + 1) * cfg.L                       # flush burst, mimo/main.cc:941-943
-    iq, tx, nv = rub.synth_frames(cfg, 1, seed, n_taps=0, snr_db=snr, fixed_H=H, include_s0=True, lead_zeros=lead,
-                                  S1=S1, s1=s1)
+    iq, tx, nv = rub.synth_frames(cfg, 1, seed, n_taps=0 if H is not None else 3, snr_db=snr, fixed_H=H,
+                                  include_s0=True, lead_zeros=lead, S1=S1, s1=s1)
     cap = iq[0]
     # --- transmit side: the reference's framegen on the same symbols
     tab = orc.modulate_table(cfg.q)
-    syms = np.ascontiguousarray(tab[tx[0]].transpose(1, 0, 2)[:8])      # [D'][2][Mo], first 8 packets
+    syms = np.ascontiguousarray(tab[tx[0]].transpose(1, 0, 2)[:8 if M <= 512 else 2])  # [D'][2][Mo], first packets
     ref_tx = ref_framegen(M, cp, nac, p, syms)
     # --- receive side: the reference's framesync on the capture
     ref = ref_framesync(M, cp, nac, p, cap, cfg.Mo, D + 8)
@@ -115,7 +119,8 @@ def report(name, r):
 
 def main():
     check = "--check" in sys.argv
-    for name in CASES:
+    only = [a for a in sys.argv[1:] if not a.startswith("--")]
+    for name in (only or CASES):
         r = run_case(name)
         report(name, r)
         if check:
@@ -126,10 +131,11 @@ def main():
         np.savez_compressed(
             os.path.join(ROOT, "tests", "golden", name + ".npz"),
             M=r["cfg"].M, cp_len=r["cfg"].cp_len, nac=r["cfg"].nac, D=r["cfg"].D, sctype=r["p"],
-            seed=CASES[name][4], snr_db=CASES[name][5], H=np.asarray(CASES[name][6], np.complex64), lead=r["lead"],
+            seed=CASES[name][4], snr_db=CASES[name][5], n_taps=0 if CASES[name][6] is not None else 3,
+            H=np.asarray(CASES[name][6] if CASES[name][6] is not None else [[0, 0], [0, 0]], np.complex64), lead=r["lead"],
             state=ref["state"], sync_index=ref["sync_index"], num_samples_processed=ref["num_samples_processed"],
             plateau_start=np.asarray(ref["plateau_start"]), plateau_end=np.asarray(ref["plateau_end"]), symbols=n,
-            G=ref["G"], eq_head=eq[:, :16], eq_tail=eq[:, -4:], eq_sha256=hashlib.sha256(eq.tobytes()).hexdigest(),
+            G=ref["G"], eq_head=eq[:, :16 if r["cfg"].M <= 512 else 4], eq_tail=eq[:, -4:], eq_sha256=hashlib.sha256(eq.tobytes()).hexdigest(),
             eq_sha256_D=hashlib.sha256(np.ascontiguousarray(eq[:, :r["cfg"].D]).tobytes()).hexdigest(),
             syms=r["syms"], ref_tx=r["ref_tx"], cap_sha256=hashlib.sha256(r["cap"].tobytes()).hexdigest())
         print("   wrote tests/golden/" + name + ".npz")

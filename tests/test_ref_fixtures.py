@@ -16,7 +16,7 @@ from oracle import orc
 from util import to_orc
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
-NAMES = ["ref_c1_m64", "ref_m256"]
+NAMES = ["ref_c1_m64", "ref_m256", "ref_m512_multipath", "ref_m2048_default"]
 
 
 def _load(name):
@@ -25,8 +25,10 @@ def _load(name):
                      num_data_symbols=int(z["D"]), sctype=z["sctype"])
     S1, s1 = rub.default_S1(cfg)
     S0, s0 = rub.default_S0(cfg)
-    iq, tx, nv = rub.synth_frames(cfg, 1, int(z["seed"]), n_taps=0, snr_db=float(z["snr_db"]), fixed_H=z["H"],
-                                  include_s0=True, lead_zeros=int(z["lead"]), S1=S1, s1=s1)
+    n_taps = int(z["n_taps"])
+    iq, tx, nv = rub.synth_frames(cfg, 1, int(z["seed"]), n_taps=n_taps, snr_db=float(z["snr_db"]),
+                                  fixed_H=None if n_taps else z["H"], include_s0=True, lead_zeros=int(z["lead"]),
+                                  S1=S1, s1=s1)
     cap = iq[0]
     assert hashlib.sha256(cap.tobytes()).hexdigest() == str(z["cap_sha256"]), "the synthetic capture changed"
     return z, cfg, S0, s0, S1, cap, tx[0]
@@ -42,7 +44,8 @@ def test_oracle_reproduces_the_reference_receiver_bit_for_bit(name):
     assert list(r["plateau_start"]) == list(z["plateau_start"]) and list(r["plateau_end"]) == list(z["plateau_end"])
     assert r["symbols_decoded"] == int(z["symbols"])
     assert np.array_equal(r["G"].view(np.uint32), z["G"].view(np.uint32))            # LS estimate incl. quirks Q1/Q2
-    assert np.array_equal(r["eq"][:, :16].view(np.uint32), z["eq_head"].view(np.uint32))
+    nh = z["eq_head"].shape[1]
+    assert np.array_equal(r["eq"][:, :nh].view(np.uint32), z["eq_head"].view(np.uint32))
     # every decoded symbol: the reference decodes past D (quirk Q14), the hash covers the D both keep
     assert r["eq"].shape[1] == cfg.D
     assert hashlib.sha256(np.ascontiguousarray(r["eq"]).tobytes()).hexdigest() == str(z["eq_sha256_D"])
@@ -82,7 +85,8 @@ def test_cuda_chain_reproduces_the_reference_receiver_bit_for_bit(name):
     G = np.ascontiguousarray(out["G"].cpu().numpy()[0].transpose(2, 0, 1))                                    # -> [k][rx][tx]
     assert np.array_equal(G.view(np.uint32), z["G"].view(np.uint32))
     eq = out["eq"].cpu().numpy()[0]                                                     # [N][D][Mo]
-    assert np.array_equal(eq[:, :16].view(np.uint32), z["eq_head"].view(np.uint32))
+    nh = z["eq_head"].shape[1]
+    assert np.array_equal(eq[:, :nh].view(np.uint32), z["eq_head"].view(np.uint32))
     assert hashlib.sha256(np.ascontiguousarray(eq).tobytes()).hexdigest() == str(z["eq_sha256_D"])   # all D symbols
 
 
