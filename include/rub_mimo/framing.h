@@ -352,8 +352,10 @@ class framesync {
     // LS + invert + decode on the GPU: one frame, per-link windows (Q2), payload start from rx
     // stream 1's last access code (Q4, framing.cc:857), identity-initialised G (Q1)
     const int32_t payload_start = corr_indices[(size_t)(num_streams > 1 ? 1 : 0) * max_ac_id + max_ac_id - 1] + (int32_t)M;
-    unsigned int nsym = (unsigned int)((Wlen - (size_t)payload_start) / symbol_len);
-    const unsigned int D = nsym < pid_max ? nsym : pid_max;
+    // every whole symbol between the payload start and the end of the window is decoded and handed
+    // to the callback, as upstream does (framing.cc:856-868): a couple more than PID_MAX, which
+    // main.cc's callback ignores (quirk Q14, main.cc:105-108)
+    const unsigned int D = (unsigned int)((Wlen - (size_t)payload_start) / symbol_len);
     if (D == 0) return;
     rub_config c = rub_detail::make_config(M, cp_len, num_streams, num_access_codes, D, 2, p.data());
     rub_rx_destroy(rx);
@@ -387,8 +389,6 @@ class framesync {
       for (unsigned int s = 0; s < num_streams; s++) X[s] = eq.data() + ((size_t)s * D + d) * M_occupied;
       callback(X, M_occupied);
     }
-    // quirk Q14: upstream keeps firing the callback for symbols beyond PID_MAX (main.cc:105-108
-    // ignores them); they carry no payload and are not decoded here
   }
 };
 

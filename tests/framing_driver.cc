@@ -1,13 +1,18 @@
-// oracle/ref_driver.cc — drives the REFERENCE's own framing code (mimo/framing.cc, compiled where it
-// lies against the stand-in headers of oracle/shim/) the way mimo/main.cc does (:1262-1300, the
-// rx loop :1003-1013 and the callback :1384-1421), behind a C interface the fixture generator
-// (oracle/make_ref_fixtures.py) loads with ctypes.  Test infrastructure only.
+// tests/framing_driver.cc — a caller written against the framing.h class API, the way mimo/main.cc
+// uses it (:1262-1300, the rx loop :1003-1013 and the callback :1384-1421), behind a C interface
+// that Python loads with ctypes.  The SAME source is compiled twice:
+//   * against the REFERENCE's own mimo/framing.h + framing.cc (oracle/Makefile `ref`, with the
+//     stand-in headers of oracle/shim/) -> oracle/_ref/libref_framing.so, which produced
+//     tests/golden/ref_*.npz (oracle/make_ref_fixtures.py);
+//   * against the product's facade include/rub_mimo/framing.h + librubmimo_b200.so
+//     (tests/test_ref_fixtures.py), which must give the same outputs: the drop-in claim.
+// Test infrastructure only.
 #include <stdint.h>
 #include <string.h>
 
 #include <vector>
 
-#include "framing.h"  // the reference's, -I/root/reference/mimo
+#include "framing.h"  // the reference's (-I/root/reference/mimo) or the facade (-Iinclude/rub_mimo)
 
 namespace {
 struct Sink { float *eq; unsigned max_syms, syms, Mo, N; } g_sink;

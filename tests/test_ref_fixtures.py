@@ -100,3 +100,70 @@ def test_gpu_framegen_reproduces_the_reference_waveform(name):
     rx = rub.Receiver(cfg.replace(num_data_symbols=ntx), S1)
     got = rx.framegen_batch(torch.from_numpy(np.ascontiguousarray(tx[None, :, :ntx])).cuda()).cpu().numpy()[0]
     assert np.array_equal(got, z["ref_tx"][:, cfg.L:])          # value-identical (signed zeros aside)
+
+
+# ---- the drop-in claim: ONE caller source (tests/framing_driver.cc, written against the framing.h
+# class API like mimo/main.cc), compiled against the reference gave the fixtures; compiled against
+# the product's facade + librubmimo_b200.so it must give the same outputs -------------------------
+import ctypes as C
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class _SyncResult(C.Structure):
+    _fields_ = [("state", C.c_int32), ("sync_index", C.c_uint64), ("num_samples_processed", C.c_uint64),
+                ("plateau_start", C.c_uint64 * 2), ("plateau_end", C.c_uint64 * 2), ("symbols", C.c_uint32)]
+
+
+@pytest.fixture(scope="module")
+def facade_driver(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("drv") / "libfacade_driver.so")
+    libdir = os.path.join(ROOT, "rub_mimo_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-w", "-I", os.path.join(ROOT, "include", "rub_mimo"),
+                           "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "framing_driver.cc"), "-o", out,
+                           "-L", libdir, "-lrubmimo_b200", f"-Wl,-rpath,{libdir}"])
+    return C.CDLL(out)
+
+
+def _vp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_same_caller_on_the_facade_transmit_side(facade_driver, name):
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    M, cp, nac = int(z["M"]), int(z["cp_len"]), int(z["nac"])
+    p = np.zeros(M, np.uint8)
+    n = [C.c_uint(), C.c_uint(), C.c_uint()]
+    facade_driver.ref_default_sctype(C.c_uint(M), _vp(p), C.byref(n[0]), C.byref(n[1]), C.byref(n[2]))
+    assert np.array_equal(p, z["sctype"])
+    syms = np.ascontiguousarray(z["syms"])
+    D, _, Mo = syms.shape
+    tx = np.zeros((2, (nac * 2 + 1 + D) * (M + cp)), np.complex64)
+    assert facade_driver.ref_framegen(C.c_uint(M), C.c_uint(cp), C.c_uint(nac), _vp(p), _vp(syms), C.c_uint(D), C.c_uint(Mo),
+                                      _vp(tx)) == tx.shape[1]
+    assert np.array_equal(tx, z["ref_tx"])                       # value-identical (signed zeros aside)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", NAMES)
+def test_same_caller_on_the_facade_receive_side(facade_driver, name):
+    z, cfg, S0, s0, S1, cap, tx = _load(name)
+    cap = [np.ascontiguousarray(r) for r in cap]
+    res = _SyncResult()
+    max_syms = cfg.D + 8
+    G = np.zeros((cfg.M, 2, 2), np.complex64)
+    eq = np.zeros((2, max_syms, cfg.Mo), np.complex64)
+    p = np.ascontiguousarray(z["sctype"])
+    facade_driver.ref_framesync(C.c_uint(cfg.M), C.c_uint(cfg.cp_len), C.c_uint(cfg.nac), _vp(p), _vp(cap[0]), _vp(cap[1]),
+                                C.c_uint64(cap[0].size), C.c_uint(4096), C.byref(res), _vp(G), _vp(eq), C.c_uint(max_syms),
+                                C.c_uint(cfg.Mo))
+    assert res.state == int(z["state"]) == 3
+    assert res.sync_index == int(z["sync_index"]) and res.num_samples_processed == int(z["num_samples_processed"])
+    assert list(res.plateau_start) == list(z["plateau_start"]) and list(res.plateau_end) == list(z["plateau_end"])
+    assert res.symbols == int(z["symbols"])
+    assert np.array_equal(G.view(np.uint32), z["G"].view(np.uint32))
+    nh = z["eq_head"].shape[1]
+    assert np.array_equal(eq[:, :nh].view(np.uint32), z["eq_head"].view(np.uint32))
+    assert hashlib.sha256(np.ascontiguousarray(eq[:, :cfg.D]).tobytes()).hexdigest() == str(z["eq_sha256_D"])
