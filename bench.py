@@ -162,7 +162,7 @@ def run_reference(args):
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["label"], "frames_per_step": nf,
-                   "note": "reference binary unbuildable here; oracle port (own radix FFT, no FFTW)"},
+                   "note": "the reference's own framing.cc (oracle/_ref, built against stand-in headers) is 2x2 / ZF only and pins parity; it cannot run this 4x4 MMSE workload, so the oracle port (own radix FFT, no FFTW) is timed"},
         "cpu_baseline": {"value": msps, "unit": "Msamples/s", "cores": cores, "kind": "port",
                          "sample": f"{nf} frames of the {wl['preset']} workload per step, OpenMP over frames"},
         "e2e": {"value": msps, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
