@@ -136,9 +136,11 @@ def cpu_oracle_rate(cfg, S1, iq, tx, n_threads, reps=3):
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation cannot be compiled here (FFTW3f,
-    liquid-dsp, VOLK, UHD, Boost, GNU Radio absent), so this arm times the oracle port of its
-    algorithm (own radix FFT instead of FFTW) on all host cores, on a bounded sample."""
+    """--impl reference: the reference's own framing.cc only builds against stand-in headers
+    (oracle/_ref; FFTW3f, liquid-dsp, VOLK, UHD, Boost, GNU Radio are absent), is 2x2 / ZF only and
+    sample-serial, so it pins parity (tests/test_ref_fixtures.py) but cannot run this workload: this
+    arm times the oracle port of its algorithm (own radix FFT instead of FFTW) on all host cores,
+    on a bounded sample."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
