@@ -117,8 +117,32 @@ def report(name, r):
     print(f"   framegen: max|tx_ref - tx_ours| = {np.abs(r['ref_tx'] - mine).max():.3e} (bit-equal: {np.array_equal(r['ref_tx'], mine)})")
 
 
+def invert_fixture(check):
+    """invert() of the reference (mimo/framing.cc:1344-1367) on seeded 2x2 matrices, including
+    badly conditioned and tiny ones."""
+    rng = np.random.default_rng(0xA3)
+    G = (rng.standard_normal((96, 2, 2)) + 1j * rng.standard_normal((96, 2, 2))).astype(np.complex64)
+    G[32:48] *= np.float32(1e-3)
+    G[48:64, 1] = G[48:64, 0] * np.complex64(1 + 1e-3j)          # nearly singular
+    G[64:80] = (np.eye(2) * 0.25 + 1e-3).astype(np.complex64)     # the identity-biased estimate of quirk Q1
+    W = np.zeros_like(G)
+    gain = np.zeros(96, np.float32)
+    ref_lib().ref_invert(_p(G), _p(W), _p(gain), C.c_uint(96))
+    mine_W = np.zeros_like(G)
+    mine_g = np.zeros(96, np.float32)
+    for i in range(96):
+        mine_W[i], mine_g[i] = rub.invert_2x2(G[i])
+    print(f"== ref_invert: W bit-equal {np.array_equal(W.view(np.uint32), mine_W.view(np.uint32))}, "
+          f"gain bit-equal {np.array_equal(gain.view(np.uint32), mine_g.view(np.uint32))}")
+    if not check:
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_invert.npz"), G=G, W=W, gain=gain)
+        print("   wrote tests/golden/ref_invert.npz")
+
+
 def main():
     check = "--check" in sys.argv
+    if "--no-invert" not in sys.argv:
+        invert_fixture(check)
     only = [a for a in sys.argv[1:] if not a.startswith("--")]
     for name in (only or CASES):
         r = run_case(name)

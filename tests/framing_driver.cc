@@ -41,6 +41,18 @@ struct ref_sync_result {
   uint32_t symbols;
 };
 
+// invert() (mimo/framing.cc:1344-1367) on n 2x2 matrices, row-major complex64 in and out
+void ref_invert(const float *G, float *W, float *gain, unsigned n) {
+  for (unsigned i = 0; i < n; i++) {
+    std::vector<std::vector<gr_complex> > g(2, std::vector<gr_complex>(2)), w(2, std::vector<gr_complex>(2));
+    for (unsigned r = 0; r < 2; r++)
+      for (unsigned c = 0; c < 2; c++) g[r][c] = gr_complex(G[2 * (4 * i + 2 * r + c)], G[2 * (4 * i + 2 * r + c) + 1]);
+    gain[i] = invert(w, g);
+    for (unsigned r = 0; r < 2; r++)
+      for (unsigned c = 0; c < 2; c++) { W[2 * (4 * i + 2 * r + c)] = w[r][c].real(); W[2 * (4 * i + 2 * r + c) + 1] = w[r][c].imag(); }
+  }
+}
+
 // the reference's default allocation (mimo/framing.cc:949-1008) and its count
 void ref_default_sctype(unsigned M, unsigned char *p, unsigned *n_null, unsigned *n_pilot, unsigned *n_data) {
   ofdmframe_init_default_sctype(p, M);
