@@ -44,3 +44,47 @@ def run(M, cp, nac, D, reps=5):
 if __name__ == "__main__":
     run(64, 16, 20, 100)
     run(2048, 152, 20, 14)
+
+
+def loop_vs_reference(name="ref_m2048_default"):
+    """The whole receive loop of mimo/main.cc on one capture (framesync::execute in 4096-sample
+    chunks: Schmidl & Cox, access-code buffering, timing search, LS estimate, invert, decode of
+    ~1000 OFDM symbols): the SAME caller source (tests/framing_driver.cc) linked against the
+    reference's own framing.cc (oracle/_ref, stand-in FFT/VOLK/liquid) and against the facade +
+    librubmimo_b200.so."""
+    import ctypes as C, os, subprocess, tempfile
+    import test_ref_fixtures as t
+    root = os.getcwd()
+    z, cfg, S0, s0, S1, cap, tx = t._load(name)
+    cap = [np.ascontiguousarray(r) for r in cap]
+    libs = {}
+    ref_so = os.path.join(root, "oracle", "_ref", "libref_framing.so")
+    if os.path.exists(ref_so):
+        libs["reference framing.cc (1 host thread)"] = C.CDLL(ref_so)
+    out = os.path.join(tempfile.mkdtemp(), "libfacade_driver.so")
+    libdir = os.path.join(root, "rub_mimo_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-w", "-I", os.path.join(root, "include", "rub_mimo"),
+                           "-I", os.path.join(root, "include"), os.path.join(root, "tests", "framing_driver.cc"), "-o", out,
+                           "-L", libdir, "-lrubmimo_b200", f"-Wl,-rpath,{libdir}"])
+    libs["facade + CUDA library"] = C.CDLL(out)
+    res = {"capture": name, "samples_per_stream": int(cap[0].size)}
+    for label, lib in libs.items():
+        best = None
+        for _ in range(2 if "reference" in label else 4):
+            r = t._SyncResult()
+            G = np.zeros((cfg.M, 2, 2), np.complex64)
+            eq = np.zeros((2, cfg.D + 8, cfg.Mo), np.complex64)
+            p = np.ascontiguousarray(z["sctype"])
+            t0 = time.perf_counter()
+            lib.ref_framesync(C.c_uint(cfg.M), C.c_uint(cfg.cp_len), C.c_uint(cfg.nac), t._vp(p), t._vp(cap[0]), t._vp(cap[1]),
+                              C.c_uint64(cap[0].size), C.c_uint(4096), C.byref(r), t._vp(G), t._vp(eq), C.c_uint(cfg.D + 8),
+                              C.c_uint(cfg.Mo))
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+            assert r.state == 3 and r.symbols == int(z["symbols"])
+        res[label + " [s]"] = round(best, 4)
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    loop_vs_reference()
