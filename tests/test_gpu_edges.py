@@ -122,3 +122,35 @@ def test_null_arguments_are_rejected():
     S1 = np.ones((cfg.N, cfg.nac, cfg.M), np.complex64) * 0.5   # not BPSK
     st = rub.lib().rub_rx_create(C.byref(h), C.byref(cfg.c), S1.ctypes.data_as(C.c_void_p), -1, None)
     assert st == rub.ERR_UNSUPPORTED
+
+
+def test_handle_lifecycle_does_not_leak_device_memory():
+    """create -> fused + staged + sync + framegen calls -> destroy, 30 times: free device memory is stable."""
+    import torch
+    cfg = rub.Config(M=512, cp_len=36, num_streams=2, num_access_codes=2, num_data_symbols=4,
+                     modulation=rub.MOD_QAM16, detector=rub.DET_ZF)
+    cfg, S1, iq, tx = make_case(cfg, 8, seed=21, n_taps=2, snr_db=25.0)
+    d_iq, d_tx = torch.from_numpy(iq).cuda(), torch.from_numpy(tx).cuda()
+
+    def cycle():
+        rx = rub.Receiver(cfg, S1)
+        for path in (rub.PATH_FUSED, rub.PATH_STAGED):
+            rx.set_path(path)
+            rx.process_batch(d_iq, out_mask=rub.OUT_EQ | rub.OUT_LLR | rub.OUT_BITS, tx_data=d_tx)
+        rx.sync()
+        rx.sc_metric(iq[0, 0])
+        rx.timing_search(np.ascontiguousarray(iq[0]))
+        rx.framegen_batch(d_tx)
+        torch.cuda.synchronize()
+        rx.close()
+
+    cycle()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    free0, _ = torch.cuda.mem_get_info()
+    for _ in range(30):
+        cycle()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    free1, _ = torch.cuda.mem_get_info()
+    assert free0 - free1 < (8 << 20), f"leaked {(free0 - free1) >> 20} MiB over 30 handle lifecycles"
