@@ -345,6 +345,22 @@ typedef struct rub_file_job {
  * not an error, the run stops at the last complete frame.                                    */
 rub_status rub_rx_process_files(rub_rx *h, const rub_file_job *job, uint64_t *frames_done);
 
+/* Multi-burst capture (rows f1/f2 put together: no pre-aligned frames): the reference's receive
+ * loop — framesync::execute with Schmidl & Cox plateau search, access-code buffering, timing
+ * search, LS estimate, invert and decode (framing.cc:471-506, :591-651, :653-886) — over a HOST
+ * capture [N][n_samples] complex64 that may hold any number of bursts.  The metric, one batched
+ * timing search over all bursts found and one batched decode run on the GPU; the decode reads the
+ * capture in place through per-link timing tables (quirks Q2/Q4).  `out` supplies HOST buffers
+ * sized for max_frames bursts in the layouts of rub_rx_io (iq / layout / timing / payload_start
+ * are ignored; tx_data, if given, enables the counters; out->counters, if given, receives the
+ * handle's counters).  sync_index[f] (may be NULL) = mean plateau start of burst f in capture
+ * samples.  Bursts whose window would start before the capture or run past its end are skipped.
+ * After a burst the search restarts behind its window (the reference stops at the first burst
+ * and is reset by its caller).  Synchronous.                                               */
+rub_status rub_rx_process_capture(rub_rx *h, const float *capture, uint64_t n_samples,
+                                  float threshold, uint32_t max_frames, const rub_rx_io *out,
+                                  uint32_t *n_found, uint64_t *sync_index);
+
 /* ------------------------------------------- configuration front-end (row f4) ------ */
 /* The fields of the reference's `options` struct (mimo/main.cc:129-156) that are not part of
  * rub_config: the offline path carries them so that a command line / GUI record written for the

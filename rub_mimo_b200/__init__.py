@@ -108,7 +108,7 @@ ABI_SYMBOLS = [
     "rub_rx_sync", "rub_rx_set_path", "rub_rx_get_path", "rub_rx_reset_counters",
     "rub_rx_device_counters", "rub_rx_read_counters", "rub_rx_launch_count", "rub_rx_last_timing",
     "rub_rx_algorithmic_bytes", "rub_rx_sc_metric", "rub_rx_timing_search", "rub_rx_set_S0",
-    "rub_framegen_batch_device", "rub_rx_process_files", "rub_config_from_args", "rub_config_from_json",
+    "rub_framegen_batch_device", "rub_rx_process_files", "rub_config_from_args", "rub_config_from_json", "rub_rx_process_capture",
     "rub_comm_get_unique_id", "rub_comm_init", "rub_allreduce_counters",
     "rub_comm_destroy", "rub_shard_range", "rub_msequence_init", "rub_msequence_reset",
     "rub_msequence_advance", "rub_msequence_generate_symbol", "rub_ofdmframe_init_default_sctype",
@@ -589,6 +589,31 @@ class Receiver:
         io.out_mask = out_mask
         _check(lib().rub_rx_process_batch_host(self.h, C.byref(io), n_frames))
         return out
+
+    # -- multi-burst capture (f1 + f2 + decode) --
+    def process_capture(self, capture, max_frames, threshold=0.95, out_mask=OUT_EQ | OUT_RXDATA, tx_data=None):
+        """capture: numpy complex64 [N][n].  Returns (n_found, sync_index[n_found], outputs dict of numpy
+        arrays sized for the bursts found)."""
+        cfg = self.cfg
+        capture = np.ascontiguousarray(capture, np.complex64)
+        assert capture.shape[0] == cfg.N
+        out = self.alloc_outputs_host(max_frames, out_mask, pinned=False)
+        tx_data = None if tx_data is None else np.ascontiguousarray(tx_data, np.uint8)
+        cnt = np.zeros((cfg.N, 4), np.uint64)
+        io = rub_rx_io()
+        io.tx_data = tx_data.ctypes.data if tx_data is not None else None
+        for k in ("eq", "llr", "bits", "rx_data", "G"):
+            setattr(io, k, out[k].ctypes.data if k in out else None)
+        io.counters = cnt.ctypes.data
+        io.out_mask = out_mask
+        found = C.c_uint32()
+        sync = np.zeros(max_frames, np.uint64)
+        _check(lib().rub_rx_process_capture(self.h, _p(capture), C.c_uint64(capture.shape[1]), C.c_float(threshold),
+                                            C.c_uint32(max_frames), C.byref(io), C.byref(found), _p(sync)))
+        n = found.value
+        res = {k: v[:n] for k, v in out.items() if not k.startswith("_")}
+        res["counters"] = cnt
+        return n, sync[:n], res
 
     # -- offline IQ-file driver (f3) --
     def process_files(self, rx_paths, n_frames, first_sample=0, frame_stride=0, tx_data_paths=None, eq_paths=None,

@@ -54,7 +54,10 @@ __global__ void __launch_bounds__(256) k_sc_metric(const cf *__restrict__ x, uns
 // (corr bits << 32 | ~i) under atomicMax: the largest correlation wins and, among equals, the
 // smallest offset — the reference's strict '>' scan in ascending i (framing.cc:717, :736).
 // Key 0 (nothing above 0) leaves the reference's initial index 0.
+// blockIdx.z = frame of a batch: its window starts win_off[z] samples into every rx row (rows are
+// rx_stride apart); keys are [frame][rx][slot].
 __global__ void __launch_bounds__(256) k_timing_search(const cf *__restrict__ window, unsigned long long wlen,
+                                                       unsigned long long rx_stride, const long long *__restrict__ win_off,
                                                        const cf *__restrict__ s1, const cf *__restrict__ s0, int M,
                                                        int L, int N, int nac, unsigned long long *__restrict__ keys) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
@@ -72,7 +75,7 @@ __global__ void __launch_bounds__(256) k_timing_search(const cf *__restrict__ wi
   }
   if (slot == 0 && !s0) return;
   const int i0 = blockIdx.x * 256;
-  const cf *w = window + (size_t)r * wlen + base + i0;
+  const cf *w = window + (size_t)r * rx_stride + (win_off ? win_off[blockIdx.z] : 0) + base + i0;
   const long long avail = (long long)wlen - base - i0;  // samples of this row from w on
   for (int i = threadIdx.x; i < M; i += 256) tpl[i] = t[i];
   for (int i = threadIdx.x; i < M + 256; i += 256) xs[i] = i < avail ? w[i] : mk(0.f, 0.f);
@@ -90,7 +93,7 @@ __global__ void __launch_bounds__(256) k_timing_search(const cf *__restrict__ wi
   const float v = ax * ax + ay * ay;
   if (v > 0.f) {
     const unsigned long long key = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);
-    atomicMax(keys + blockIdx.y, key);
+    atomicMax(keys + (size_t)blockIdx.z * gridDim.y + blockIdx.y, key);
   }
 }
 

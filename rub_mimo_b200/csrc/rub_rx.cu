@@ -500,7 +500,7 @@ static rub_status run_fused(rub_rx *h, const ChainArgs &a, uint32_t n_frames, bo
   return RUB_OK;
 }
 
-static rub_status process_device(rub_rx *h, const rub_rx_io *io, uint32_t n_frames, bool timed) {
+static rub_status process_device(rub_rx *h, const rub_rx_io *io, uint32_t n_frames, bool timed, bool shared_rows = false) {
   if (!h || !io) { set_error("process_batch: NULL argument"); return RUB_ERR_INVALID_ARG; }
   if (n_frames == 0) return RUB_OK;  // an empty batch is a no-op (no launch, counters untouched)
   if (!io->iq) { set_error("process_batch: iq is NULL"); return RUB_ERR_INVALID_ARG; }
@@ -511,7 +511,8 @@ static rub_status process_device(rub_rx *h, const rub_rx_io *io, uint32_t n_fram
   ChainArgs a;
   memset(&a, 0, sizeof(a));
   a.iq = reinterpret_cast<const cf *>(io->iq);
-  a.frame_stride = frame_stride; a.rx_stride = rx_stride; a.first_sample = io->layout.first_sample;
+  // shared_rows: every frame addresses the same capture rows, the timing tables hold absolute offsets
+  a.frame_stride = shared_rows ? 0 : frame_stride; a.rx_stride = rx_stride; a.first_sample = io->layout.first_sample;
   a.timing = io->timing; a.payload_start = io->payload_start;
   a.M = c.M; a.cp = c.cp; a.L = c.L; a.N = c.N; a.nac = c.nac; a.D = c.D; a.T = c.T; a.Mo = c.Mo; a.q = c.q; a.P = c.P;
   a.n_frames = (int)n_frames; a.row_bytes = c.row_bytes;
@@ -757,7 +758,7 @@ extern "C" rub_status rub_rx_timing_search(rub_rx *h, const float *window, uint6
   if (e == cudaSuccess) e = cudaMemsetAsync(dk, 0, sizeof(unsigned long long) * nkeys, h->stream);
   if (e == cudaSuccess) {
     dim3 grid((c.L + 255) / 256, nkeys);
-    k_timing_search<<<grid, 256, smem, h->stream>>>(dw, wlen, h->d_s1, s0_corr_index ? h->d_s0 : nullptr, (int)c.M,
+    k_timing_search<<<grid, 256, smem, h->stream>>>(dw, wlen, wlen, nullptr, h->d_s1, s0_corr_index ? h->d_s0 : nullptr, (int)c.M,
                                                     (int)c.L, (int)c.N, (int)c.nac, dk);
     h->launches += 1;
     e = cudaGetLastError();
@@ -774,6 +775,149 @@ extern "C" rub_status rub_rx_timing_search(rub_rx *h, const float *window, uint6
       if (slot == 0) { if (s0_corr_index) s0_corr_index[r] = (int32_t)i; }
       else corr_indices[r * max_ac + slot - 1] = hit ? (int32_t)(c.L * slot + i) : 0;
     }
+  return RUB_OK;
+}
+
+// ---------------------------------------------------------------- multi-frame capture -
+// The reference's receive loop (framesync::execute, mimo/framing.cc:471-506, :591-651, :653-886)
+// over a capture that holds any number of bursts: Schmidl & Cox metric on the GPU, the reference's
+// plateau rule walked over it on the host, one batched timing search for all bursts found, and one
+// batched LS / invert / decode call whose per-link timing tables address the capture in place.
+extern "C" rub_status rub_rx_process_capture(rub_rx *h, const float *capture, uint64_t n_samples, float threshold,
+                                             uint32_t max_frames, const rub_rx_io *out, uint32_t *n_found,
+                                             uint64_t *sync_index) {
+  if (n_found) *n_found = 0;
+  if (!h || !capture || !out || !n_found) { set_error("process_capture: NULL argument"); return RUB_ERR_INVALID_ARG; }
+  const HostCfg &c = h->h;
+  const uint64_t L = c.L, acb_len = L * (c.nac * c.N + 4), tx_sig_len = (uint64_t)c.D * L, Wlen = acb_len + tx_sig_len;
+  const uint32_t max_ac = c.nac * c.N, slots = max_ac + 1;
+  if (c.c.estimator != RUB_EST_LS_FULLBAND) { set_error("process_capture: TDMA access codes only"); return RUB_ERR_UNSUPPORTED; }
+  if (n_samples >= 0x7fffffffull) { set_error("process_capture: capture longer than 2^31 samples"); return RUB_ERR_INVALID_ARG; }
+  if (max_frames == 0 || n_samples < Wlen) return RUB_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  // --- capture and metric on the device
+  cf *d_cap = nullptr;
+  float *d_y = nullptr;
+  CUDA_TRY(cudaMalloc(&d_cap, sizeof(cf) * n_samples * c.N));
+  struct Guard { std::vector<void *> p; ~Guard() { for (void *q : p) cudaFree(q); } } guard;
+  guard.p.push_back(d_cap);
+  CUDA_TRY(cudaMalloc(&d_y, sizeof(float) * n_samples * c.N));
+  guard.p.push_back(d_y);
+  CUDA_TRY(cudaMemcpyAsync(d_cap, capture, sizeof(cf) * n_samples * c.N, cudaMemcpyHostToDevice, h->stream));
+  {
+    const size_t smem = (size_t)(c.M + c.M / 2 + 256) * sizeof(cf);
+    CUDA_TRY(cudaFuncSetAttribute(k_sc_metric, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (uint32_t s = 0; s < c.N; s++)
+      k_sc_metric<<<(unsigned)((n_samples + 255) / 256), 256, smem, h->stream>>>(d_cap + (size_t)s * n_samples, n_samples, (int)c.M,
+                                                                              d_y + (size_t)s * n_samples);
+    h->launches += c.N;
+    CUDA_TRY(cudaGetLastError());
+  }
+  std::vector<float> y((size_t)n_samples * c.N);
+  CUDA_TRY(cudaMemcpyAsync(y.data(), d_y, sizeof(float) * y.size(), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  // --- the plateau rule of execute_sc_sync (framing.cc:591-624) and the access-code buffering of
+  //     execute_save_access_codes (:639-651), restarted after every burst
+  std::vector<long long> win_off;
+  std::vector<uint64_t> syncs;
+  {
+    std::vector<uint64_t> pstart(c.N, 0), pend(c.N, 0);
+    std::vector<char> inpl(c.N, 0);
+    uint64_t i = 0;
+    while (i < n_samples && win_off.size() < max_frames) {
+      bool proceed = true;
+      for (uint32_t s = 0; s < c.N; s++) {
+        if (y[(size_t)s * n_samples + i] > threshold) {
+          if (inpl[s]) pend[s] = i;
+          else { inpl[s] = 1; pstart[s] = i; pend[s] = i; }
+        } else inpl[s] = 0;
+        proceed = proceed && (pend[s] - pstart[s] > c.cp) && inpl[s];
+      }
+      if (!proceed) { i++; continue; }
+      uint64_t si = 0;
+      for (uint32_t s = 0; s < c.N; s++) si += pstart[s];
+      si /= c.N;
+      const uint64_t i_switch = si + tx_sig_len + acb_len - L;  // first sample that is not buffered
+      if (i_switch > n_samples) break;                           // the burst runs past the capture
+      if (i_switch >= Wlen) { win_off.push_back((long long)(i_switch - Wlen)); syncs.push_back(si); }
+      std::fill(inpl.begin(), inpl.end(), 0);
+      i = i_switch + 1;
+    }
+  }
+  const uint32_t F = (uint32_t)win_off.size();
+  if (F == 0) return RUB_OK;
+  // --- batched timing search (framing.cc:702-744) straight from the capture rows
+  long long *d_off = nullptr;
+  unsigned long long *d_keys = nullptr;
+  CUDA_TRY(cudaMalloc(&d_off, sizeof(long long) * F));
+  guard.p.push_back(d_off);
+  CUDA_TRY(cudaMalloc(&d_keys, sizeof(unsigned long long) * (size_t)F * c.N * slots));
+  guard.p.push_back(d_keys);
+  CUDA_TRY(cudaMemcpyAsync(d_off, win_off.data(), sizeof(long long) * F, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemsetAsync(d_keys, 0, sizeof(unsigned long long) * (size_t)F * c.N * slots, h->stream));
+  {
+    const size_t smem = (size_t)(2 * c.M + 256) * sizeof(cf);
+    CUDA_TRY(cudaFuncSetAttribute(k_timing_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((c.L + 255) / 256, c.N * slots, F);
+    k_timing_search<<<grid, 256, smem, h->stream>>>(d_cap, Wlen, n_samples, d_off, h->d_s1, nullptr, (int)c.M, (int)c.L,
+                                                    (int)c.N, (int)c.nac, d_keys);
+    h->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+  }
+  std::vector<unsigned long long> keys((size_t)F * c.N * slots);
+  CUDA_TRY(cudaMemcpyAsync(keys.data(), d_keys, sizeof(unsigned long long) * keys.size(), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  std::vector<int32_t> timing((size_t)F * c.N * c.T), pay(F);
+  for (uint32_t f = 0; f < F; f++) {
+    for (uint32_t r = 0; r < c.N; r++)
+      for (uint32_t ac = 0; ac < max_ac; ac++) {
+        const unsigned long long k = keys[((size_t)f * c.N + r) * slots + ac + 1];
+        const uint32_t idx = (k >> 32) ? (uint32_t)(c.L * (ac + 1)) + (0xffffffffu - (uint32_t)(k & 0xffffffffu)) : 0u;
+        timing[((size_t)f * c.N + r) * c.T + ac] = (int32_t)(win_off[f] + idx);
+      }
+    // payload start from rx stream 1's last access code (quirk Q4, framing.cc:857)
+    pay[f] = timing[((size_t)f * c.N + (c.N > 1 ? 1 : 0)) * c.T + max_ac - 1] + (int32_t)c.M;
+  }
+  // --- LS / invert / decode of all bursts in one batch, outputs gathered on the device
+  const size_t pts = (size_t)c.N * c.D * c.Mo;
+  const size_t eq_b = pts * sizeof(cf), llr_b = pts * c.q * sizeof(float), bits_b = (size_t)c.N * c.D * c.row_bytes,
+               rd_b = pts, g_b = (size_t)c.N * c.N * c.M * sizeof(cf), tx_b = pts;
+  int32_t *d_tim = nullptr, *d_pay = nullptr;
+  CUDA_TRY(cudaMalloc(&d_tim, sizeof(int32_t) * timing.size())); guard.p.push_back(d_tim);
+  CUDA_TRY(cudaMalloc(&d_pay, sizeof(int32_t) * F)); guard.p.push_back(d_pay);
+  CUDA_TRY(cudaMemcpyAsync(d_tim, timing.data(), sizeof(int32_t) * timing.size(), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(d_pay, pay.data(), sizeof(int32_t) * F, cudaMemcpyHostToDevice, h->stream));
+  rub_rx_io d;
+  memset(&d, 0, sizeof(d));
+  d.iq = reinterpret_cast<const float *>(d_cap);
+  d.layout.rx_stride = n_samples;
+  d.timing = d_tim;
+  d.payload_start = d_pay;
+  d.out_mask = out->out_mask;
+  auto dev_out = [&](size_t bytes, void **p) -> rub_status { CUDA_TRY(cudaMalloc(p, bytes * F)); guard.p.push_back(*p); return RUB_OK; };
+  rub_status st = RUB_OK;
+  if (!st && (out->out_mask & RUB_OUT_EQ)) st = dev_out(eq_b, (void **)&d.eq);
+  if (!st && (out->out_mask & RUB_OUT_LLR)) st = dev_out(llr_b, (void **)&d.llr);
+  if (!st && (out->out_mask & RUB_OUT_BITS)) st = dev_out(bits_b, (void **)&d.bits);
+  if (!st && (out->out_mask & RUB_OUT_RXDATA)) st = dev_out(rd_b, (void **)&d.rx_data);
+  if (!st && (out->out_mask & RUB_OUT_G)) st = dev_out(g_b, (void **)&d.G);
+  if (!st && out->tx_data) {
+    uint8_t *dtx = nullptr;
+    st = dev_out(tx_b, (void **)&dtx);
+    if (!st) { CUDA_TRY(cudaMemcpyAsync(dtx, out->tx_data, tx_b * F, cudaMemcpyHostToDevice, h->stream)); d.tx_data = dtx; }
+  }
+  if (st) return st;
+  st = process_device(h, &d, F, false, /*shared_rows=*/true);
+  if (st) return st;
+  if (d.eq) CUDA_TRY(cudaMemcpyAsync(out->eq, d.eq, eq_b * F, cudaMemcpyDeviceToHost, h->stream));
+  if (d.llr) CUDA_TRY(cudaMemcpyAsync(out->llr, d.llr, llr_b * F, cudaMemcpyDeviceToHost, h->stream));
+  if (d.bits) CUDA_TRY(cudaMemcpyAsync(out->bits, d.bits, bits_b * F, cudaMemcpyDeviceToHost, h->stream));
+  if (d.rx_data) CUDA_TRY(cudaMemcpyAsync(out->rx_data, d.rx_data, rd_b * F, cudaMemcpyDeviceToHost, h->stream));
+  if (d.G) CUDA_TRY(cudaMemcpyAsync(out->G, d.G, g_b * F, cudaMemcpyDeviceToHost, h->stream));
+  if (out->counters) CUDA_TRY(cudaMemcpyAsync(out->counters, h->d_counters, sizeof(uint64_t) * 4 * c.N, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (sync_index) for (uint32_t f = 0; f < F; f++) sync_index[f] = syncs[f];
+  *n_found = F;
   return RUB_OK;
 }
 
