@@ -463,7 +463,7 @@ class Receiver:
         _check(lib().rub_rx_create(C.byref(self.h), C.byref(cfg.c), _p(S1), dev, stream))
 
     def close(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and lib is not None:   # `lib` is gone during interpreter shutdown
             lib().rub_rx_destroy(self.h)
             self.h = None
 

@@ -151,8 +151,8 @@ struct FusedTraits {
                                                   // block are served by one warp (Y is read once)
   static constexpr int KSTEP = 64 * NWARPS;       // carrier distance between a warp's blocks
   static constexpr int BUF_ELEMS = N * PAD;
-  // small CTAs share an SM: cap their registers so that 512 threads fit (4 x 128 threads x 128 registers)
-  static constexpr int MIN_CTAS = THREADS <= 128 ? 4 : 1;
+  // small CTAs share an SM: cap their registers so that 512 threads fit (4 x 128 or 2 x 256 threads x 128 registers)
+  static constexpr int MIN_CTAS = THREADS <= 128 ? 4 : (THREADS <= 256 ? 2 : 1);
   static_assert(NT % 32 == 0, "fused path needs NT to be whole warps");
   static_assert(KPW >= 1 && KPW * N * NWARPS == TASKS && (TPW % 2) == 0, "task split");
   static size_t smem_bytes(int q) {
