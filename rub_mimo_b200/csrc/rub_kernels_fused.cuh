@@ -153,11 +153,15 @@ struct FusedTraits {
   static constexpr int BUF_ELEMS = N * PAD;
   // small CTAs share an SM: cap their registers so that 512 threads fit (4 x 128 or 2 x 256 threads x 128 registers)
   static constexpr int MIN_CTAS = THREADS <= 128 ? 4 : (THREADS <= 256 ? 2 : 1);
+  // the 4096-point stage tables (32 KB) stay in global memory / L1 for the 256-thread instance so that
+  // two of its CTAs fit an SM; everywhere else they are copied to shared memory once
+  static constexpr bool TW_SMEM = !(LOG2M == 12 && THREADS <= 256);
+  static constexpr int TW_SMEM_ELEMS = TW_SMEM ? FftTw<LOG2M>::TOTAL : 0;
   static_assert(NT % 32 == 0, "fused path needs NT to be whole warps");
   static_assert(KPW >= 1 && KPW * N * NWARPS == TASKS && (TPW % 2) == 0, "task split");
   static size_t smem_bytes(int q) {
     return (size_t)2 * BUF_ELEMS * sizeof(cf) + (size_t)NWARPS * 2 * (256 * q + 64) + 64 * sizeof(float2) +
-           (size_t)FftTw<LOG2M>::TOTAL * sizeof(cf) + (size_t)2 * N * M /* tx_data */ + 64 /* mbarriers */ + 8 * N * 2 + 64;
+           (size_t)TW_SMEM_ELEMS * sizeof(cf) + (size_t)2 * N * M /* tx_data */ + 64 /* mbarriers */ + 8 * N * 2 + 64;
   }
 };
 
@@ -375,7 +379,7 @@ __global__ void __launch_bounds__(FusedTraits<LOG2M, N>::THREADS, FusedTraits<LO
   const int stage_stride = fa.llr_stage_bytes + 64;  // llr block followed by 64 B of packed bits
   float2 *lut = reinterpret_cast<float2 *>(stage_base + (size_t)NWARPS * 2 * stage_stride);
   cf *tw_s = reinterpret_cast<cf *>(lut + 64);  // stage twiddles, copied once
-  unsigned char *txbuf = reinterpret_cast<unsigned char *>(tw_s + TW::TOTAL);  // [2][N][M] tx symbols
+  unsigned char *txbuf = reinterpret_cast<unsigned char *>(tw_s + TR::TW_SMEM_ELEMS);  // [2][N][M] tx symbols
   unsigned long long *mbar = reinterpret_cast<unsigned long long *>(txbuf + 2 * N * M);  // full[2], empty[2]
   unsigned *cnt = reinterpret_cast<unsigned *>(mbar + 4);  // [N][2] bit errors, symbol errors
 
@@ -387,7 +391,8 @@ __global__ void __launch_bounds__(FusedTraits<LOG2M, N>::THREADS, FusedTraits<LO
   const unsigned long long pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
 
   if (tid < 64) lut[tid] = make_float2(lutp.slope[tid], lutp.icpt[tid]);
-  for (int i = tid; i < TW::TOTAL; i += THREADS) tw_s[i] = a.tw[i];
+  for (int i = tid; i < TR::TW_SMEM_ELEMS; i += THREADS) tw_s[i] = a.tw[i];
+  const cf *tws = TR::TW_SMEM ? tw_s : a.tw;
   if (tid < 2 * N) cnt[tid] = 0;
   if (tid == 0) {
     mbar_init(&mbar[0], 1);
@@ -482,7 +487,7 @@ __global__ void __launch_bounds__(FusedTraits<LOG2M, N>::THREADS, FusedTraits<LO
       if (PL::NSTG == 2) prefetch_task0();
       FF::S1::template load<true>(ft, mine, v);
       group_sync<NT>(1 + ant);
-      FF::S1::template compute<true>(ft, v, tw_s + TW::OFF1);
+      FF::S1::template compute<TR::TW_SMEM>(ft, v, tws + TW::OFF1);
       if (PL::NSTG == 2) {
         FF::S1::template store<false, true>(ft, v, mine, scale);
       } else {
@@ -491,7 +496,7 @@ __global__ void __launch_bounds__(FusedTraits<LOG2M, N>::THREADS, FusedTraits<LO
         prefetch_task0();
         FF::S2::template load<true>(ft, mine, v);
         group_sync<NT>(1 + ant);
-        FF::S2::template compute<true>(ft, v, tw_s + TW::OFF2);
+        FF::S2::template compute<TR::TW_SMEM>(ft, v, tws + TW::OFF2);
         FF::S2::template store<false, true>(ft, v, mine, scale);
       }
     }
