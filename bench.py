@@ -206,7 +206,7 @@ def run_ours(args):
         out_mask |= {"eq": rub.OUT_EQ, "llr": rub.OUT_LLR, "bits": rub.OUT_BITS, "rx_data": rub.OUT_RXDATA}[name]
     rx = rub.Receiver(cfg, S1, device=local)
     if args.path:
-        rx.set_path({"staged": rub.PATH_STAGED, "fused": rub.PATH_FUSED, "fused32": rub.PATH_FUSED32}[args.path])
+        rx.set_path({"staged": rub.PATH_STAGED, "fused": rub.PATH_FUSED}[args.path])
     out = rx.alloc_outputs(F, out_mask)
     if world > 1:
         uid = [rub.comm_get_unique_id() if rank == 0 else None]
@@ -253,7 +253,7 @@ def run_ours(args):
         rx.sync()
         dom.append(rx.last_timing()[1])
     dom_ms = float(np.mean(dom))
-    path = {rub.PATH_STAGED: "staged", rub.PATH_FUSED: "fused", rub.PATH_FUSED32: "fused32"}[rx.last_path]
+    path = {rub.PATH_STAGED: "staged", rub.PATH_FUSED: "fused"}[rx.last_path]
     step_ms = ms / args.steps
     msps, det = metric_values(cfg, F * world, step_ms / 1e3)
     peak, peak_src = _peaks()
@@ -328,7 +328,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": (tr or {}).get("dram_bytes_per_launch"),
                          "algorithmic_bytes_per_launch": alg_dom, "kernel_ms": dom_ms,
-                         "kernel": {"fused": "k_rx_fused", "fused32": "k_rx_fused32"}.get(path, "k_detect"), "peak_source": peak_src},
+                         "kernel": {"fused": "k_rx_fused"}.get(path, "k_detect"), "peak_source": peak_src},
             "cpu_baseline": cpu,
             "e2e": e2e,
             "gpu_launches": int(launches),
@@ -349,7 +349,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
     ap.add_argument("--frames", type=int, default=0, help="frames per GPU (default: workload's)")
-    ap.add_argument("--path", default="", choices=["", "staged", "fused", "fused32"])
+    ap.add_argument("--path", default="", choices=["", "staged", "fused"])
     ap.add_argument("--outputs", default="eq+llr+bits", help="subset of eq+llr+bits+rx_data (default: all three)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

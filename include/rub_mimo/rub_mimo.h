@@ -79,8 +79,6 @@ typedef enum rub_status {
 #define RUB_PATH_AUTO 0u
 #define RUB_PATH_STAGED 1u /* FFT -> HBM -> estimate -> weights -> detect (any config)   */
 #define RUB_PATH_FUSED 2u  /* one persistent kernel per frame batch (eligible configs)   */
-#define RUB_PATH_FUSED32 3u /* the fused kernel at 32 warps/SM (4x4 / 2048 only; never
-                             chosen by AUTO, bit-identical, see rub_kernels_fused32.cuh) */
 
 /* ------------------------------------------------------------ config --------------- */
 /* Runtime mirror of the compile-time macros of mimo/config.h:65-108.                   */

@@ -391,45 +391,37 @@ uint32_t orc_demodulate(uint32_t q, ocf x) {
   return (gray_encode(s_i) << m) + gray_encode(s_q);
 }
 /* Max-log LLR (extension): LLR_b = (min_{a:b=1}|z-a|^2 - min_{a:b=0}|z-a|^2)
- * / sigma_eff^2.  For Gray square QAM it separates per axis, and inside the decision cell of
- * the sliced level a_h the nearest level with the opposite bit, a_o, is fixed, so
- * |x-a_o|^2-|x-a_h|^2 = 2(a_h-a_o) x + (a_o^2-a_h^2): one slope/intercept pair per (bit,
- * level), tabulated in double and rounded to float.                                       */
-static void llr_table(uint32_t m, float alpha, float *slope, float *icpt /* [m][P] */) {
-  uint32_t P = 1u << m;
-  for (uint32_t b = 0; b < m; b++) {
-    uint32_t p = m - 1 - b; /* bit position from the LSB of the gray code */
-    for (uint32_t s = 0; s < P; s++) {
-      uint32_t v = (gray_encode(s) >> p) & 1u;
-      uint32_t o = s & ((1u << p) - 1u);
-      uint32_t odd = (s >> p) & 1u;
-      int so = odd ? (int)(s - o) - 1 : (int)(s - o + (1u << p));
-      double ah = (double)(2 * (int)s - (int)P + 1) * (double)alpha;
-      double ao = (double)(2 * so - (int)P + 1) * (double)alpha;
-      double sg = v ? -1.0 : 1.0;
-      slope[b * P + s] = (float)(sg * 2.0 * (ah - ao));
-      icpt[b * P + s] = (float)(sg * (ao * ao - ah * ah));
-    }
-  }
-}
-static float g_slope[9][64], g_icpt[9][64];
-static int g_llr_ready[9];
-static void llr_prepare(uint32_t q) {
-#pragma omp critical(orc_llr)
-  {
-    if (!g_llr_ready[q]) { llr_table(q / 2, qam_alpha(q), g_slope[q], g_icpt[q]); g_llr_ready[q] = 1; }
+ * / sigma_eff^2, positive => bit 0.  For Gray square QAM it separates per axis and has a closed
+ * form in the folded residuals of the successive-comparison slicer: t_0 = x,
+ * t_j = |t_{j-1}| - 2^(m-j) alpha.  Axis bit j (0 = MSB) is decided by the sign of t_j inside a
+ * sub-constellation of n_j = 2^(m-1-j) levels per side, where the max-log metric is the convex
+ * piecewise-linear function
+ *     F_j(w) = max_{i=1..n_j} ( i*w - i(i-1) alpha ),  w = |t_j|,
+ * (inside the i-th cell from the boundary the nearest opposite-bit level is i cells away), so
+ *     LLR_j = -/+ 4 alpha F_j(|t_j|) / sigma_eff^2
+ * with the sign of -x for j = 0 (positive levels carry gray MSB 1) and the sign of t_j for
+ * j >= 1 (the outer half carries gray bit 0).  fp32 evaluation order (the arithmetic contract):
+ * k = (4 alpha) * isig; terms fmaf((float)i, w, -c_i) with c_i = (float)(i(i-1) * (double)alpha),
+ * max taken in ascending i starting from w; LLR = (F * k) with the sign bit xor-ed in.        */
+float orc_llr_coef(uint32_t q, uint32_t i) { return (float)((double)(i * (i - 1u)) * (double)qam_alpha(q)); }
+static void llr_axis(uint32_t m, float alpha, uint32_t q, float x, float k, float *llr) {
+  float t = x;
+  for (uint32_t j = 0; j < m; j++) {
+    if (j > 0) t = fabsf(t) - (float)(1u << (m - j)) * alpha;
+    float w = fabsf(t), F = w;
+    uint32_t n = 1u << (m - 1 - j);
+    for (uint32_t i = 2; i <= n; i++) F = fmaxf(F, fmaf((float)i, w, -orc_llr_coef(q, i)));
+    float v = F * k;
+    int neg = (j == 0) ? !signbit(t) : signbit(t);
+    llr[j] = neg ? -v : v;
   }
 }
 void orc_llr(uint32_t q, ocf x, float isig, float *llr) {
-  uint32_t m = q / 2, P = 1u << m;
+  uint32_t m = q / 2;
   float alpha = qam_alpha(q);
-  if (!g_llr_ready[q]) llr_prepare(q);
-  const float *slope = g_slope[q], *icpt = g_icpt[q];
-  uint32_t s_i = slice_axis(x.re, m, alpha), s_q = slice_axis(x.im, m, alpha);
-  for (uint32_t b = 0; b < m; b++) {
-    llr[b] = fmaf(slope[b * P + s_i], x.re, icpt[b * P + s_i]) * isig;
-    llr[m + b] = fmaf(slope[b * P + s_q], x.im, icpt[b * P + s_q]) * isig;
-  }
+  float k = (4.0f * alpha) * isig;
+  llr_axis(m, alpha, q, x.re, k, llr);
+  llr_axis(m, alpha, q, x.im, k, llr + m);
 }
 
 /* ------------------------------------------------------------ weights --------------- */
@@ -701,7 +693,6 @@ int orc_rx_batch(const orc_config *c, const ocf *S1, const ocf *iq, uint64_t fra
   const size_t per = (size_t)N * D * Mo, row_bytes = (Mo * q + 7) / 8;
   int err = 0;
   (void)get_tw(M);
-  if (q <= 8 && qam_alpha(q) != 0.f) llr_prepare(q);
 #ifdef _OPENMP
   if (n_threads < 1) n_threads = 1;
 #pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads) if (n_threads > 1)

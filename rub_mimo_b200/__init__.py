@@ -26,7 +26,7 @@ DET_ZF, DET_MMSE = 0, 1
 EST_LS_FULLBAND, EST_LS_COMB_INTERP = 0, 1
 FLAG_Q1_IDENTITY_INIT, FLAG_MMSE_UNBIASED, FLAG_ZF_CHOLESKY = 1, 2, 4
 OUT_EQ, OUT_LLR, OUT_BITS, OUT_RXDATA, OUT_G = 1, 2, 4, 8, 16
-PATH_AUTO, PATH_STAGED, PATH_FUSED, PATH_FUSED32 = 0, 1, 2, 3
+PATH_AUTO, PATH_STAGED, PATH_FUSED = 0, 1, 2
 NCCL_UNIQUE_ID_BYTES = 128
 
 

@@ -199,6 +199,65 @@ RUB_HD uint32_t slice_axis_rt(float v, int m, float alpha) {
   return s;
 }
 
+// ------------------------------------------------------------------ max-log LLR -------
+// Closed form of the max-log LLR of one axis of Gray square QAM (the oracle's orc_llr restates
+// it): folded residuals t_0 = x, t_j = |t_{j-1}| - 2^(m-j) alpha; axis bit j is decided by the
+// sign of t_j inside a sub-constellation of n_j = 2^(m-1-j) levels per side, where the metric is
+// F_j(w) = max_{i=1..n_j}(i w - i(i-1) alpha), w = |t_j|.  LLR_j = (F_j * k) with the sign of -x
+// (j = 0) or of t_j (j >= 1) xor-ed in; k = (4 alpha) / sigma_eff^2; positive => bit 0.
+struct DemapConst {
+  float alpha;   // level spacing / 2
+  int m;         // bits per axis
+  float h[4];    // h[j] = 2^(m-j) * alpha, j = 1..m-1: fold offsets = the slicer's ref[] values
+  float nc[9];   // nc[i] = -(float)(i(i-1) * (double)alpha), i = 2..8
+  float k4;      // 4 * alpha
+};
+RUB_HD uint32_t f2u(float f) {
+#if defined(__CUDA_ARCH__)
+  return __float_as_uint(f);
+#else
+  union { float f; uint32_t u; } c; c.f = f; return c.u;
+#endif
+}
+RUB_HD float u2f(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float(u);
+#else
+  union { float f; uint32_t u; } c; c.u = u; return c.f;
+#endif
+}
+template <int MB>
+RUB_HD void llr_axis(float x, float k, const DemapConst &dc, float *llr) {
+  float t = x;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int j = 0; j < MB; j++) {
+    if (j > 0) t = fabsf(t) - dc.h[j];
+    const int n = 1 << (MB - 1 - j);
+    if (n == 1) {
+      llr[j] = (j == 0 ? -t : t) * k;   // F = |t|: (|t| k) with the sign of -/+t is (-/+t) k
+    } else {
+      const float w = fabsf(t);
+      float F = w;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int i = 2; i <= n; i++) F = fmaxf(F, fmaf((float)i, w, dc.nc[i]));
+      const uint32_t sg = (j == 0 ? ~f2u(t) : f2u(t)) & 0x80000000u;
+      llr[j] = u2f(f2u(F * k) ^ sg);
+    }
+  }
+}
+RUB_HD void llr_axis_rt(float x, float k, int m, const DemapConst &dc, float *llr) {
+  switch (m) {
+    case 1: llr_axis<1>(x, k, dc, llr); break;
+    case 2: llr_axis<2>(x, k, dc, llr); break;
+    case 3: llr_axis<3>(x, k, dc, llr); break;
+    default: llr_axis<4>(x, k, dc, llr); break;
+  }
+}
+
 // ------------------------------------------------------------------ weights -----------
 // invert(), mimo/framing.cc:1344-1367 (INVERT_TO_UNITY false): W = conj(det)*adj(G),
 // returns 1/|det|^2.  Row-major 2x2.  Every product is the reference's std::complex operator*

@@ -102,30 +102,16 @@ void build_twiddles(uint32_t log2M, std::vector<cf> &master, std::vector<cf> &pa
   }
 }
 
-static uint32_t gray_enc(uint32_t s) { return s ^ (s >> 1); }
-
-// Max-log LLR table: inside the decision cell of level s the nearest level with the opposite
-// value of axis bit b is fixed, so |x-a_o|^2-|x-a_h|^2 is affine in x (DESIGN.md "Demapper").
-void build_demap_lut(uint32_t q, DemapLut &lut) {
-  const uint32_t m = q / 2, P = 1u << m;
+// Constants of the closed-form max-log demapper (rub_arith.cuh llr_axis, DESIGN.md "Demapper")
+void build_demap_const(uint32_t q, DemapConst &dc) {
+  const uint32_t m = q / 2;
   const float alpha = qam_alpha(q);
-  memset(&lut, 0, sizeof(lut));
-  lut.alpha = alpha;
-  lut.m = (int)m;
-  for (uint32_t b = 0; b < m; b++) {
-    const uint32_t p = m - 1 - b;
-    for (uint32_t s = 0; s < P; s++) {
-      const uint32_t v = (gray_enc(s) >> p) & 1u;
-      const uint32_t o = s & ((1u << p) - 1u);
-      const uint32_t odd = (s >> p) & 1u;
-      const int so = odd ? (int)(s - o) - 1 : (int)(s - o + (1u << p));
-      const double ah = (double)(2 * (int)s - (int)P + 1) * (double)alpha;
-      const double ao = (double)(2 * so - (int)P + 1) * (double)alpha;
-      const double sg = v ? -1.0 : 1.0;
-      lut.slope[b * P + s] = (float)(sg * 2.0 * (ah - ao));
-      lut.icpt[b * P + s] = (float)(sg * (ao * ao - ah * ah));
-    }
-  }
+  memset(&dc, 0, sizeof(dc));
+  dc.alpha = alpha;
+  dc.m = (int)m;
+  dc.k4 = 4.0f * alpha;
+  for (uint32_t j = 1; j < m && j < 4; j++) dc.h[j] = (float)(1u << (m - j)) * alpha;
+  for (uint32_t i = 2; i <= 8; i++) dc.nc[i] = -(float)((double)(i * (i - 1u)) * (double)alpha);
 }
 
 void host_fft_forward(uint32_t log2M, const cf *in, cf *out, const cf *tw) {

@@ -20,16 +20,9 @@ struct HostCfg {
   uint32_t row_bytes;  // ceil(Mo*q/8)
 };
 
-struct DemapLut {      // slope/intercept of the max-log LLR per (axis bit, level), [m][P]
-  float slope[64];
-  float icpt[64];
-  float alpha;
-  int m;               // bits per axis
-};
-
 rub_status host_cfg_init(HostCfg &h, const rub_config *cfg);
 void build_twiddles(uint32_t log2M, std::vector<cf> &master, std::vector<cf> &packed);
-void build_demap_lut(uint32_t q, DemapLut &lut);
+void build_demap_const(uint32_t q, DemapConst &dc);
 float qam_alpha(uint32_t q);
 // forward FFT on the host through the same stage code the kernels run (transmit side only)
 void host_fft_forward(uint32_t log2M, const cf *in, cf *out, const cf *packed_tw);

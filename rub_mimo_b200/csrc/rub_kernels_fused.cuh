@@ -160,7 +160,7 @@ struct FusedTraits {
   static_assert(NT % 32 == 0, "fused path needs NT to be whole warps");
   static_assert(KPW >= 1 && KPW * N * NWARPS == TASKS && (TPW % 2) == 0, "task split");
   static size_t smem_bytes(int q) {
-    return (size_t)2 * BUF_ELEMS * sizeof(cf) + (size_t)NWARPS * 2 * (256 * q + 64) + 64 * sizeof(float2) +
+    return (size_t)2 * BUF_ELEMS * sizeof(cf) + (size_t)NWARPS * 2 * (256 * q + 64) +
            (size_t)TW_SMEM_ELEMS * sizeof(cf) + (size_t)2 * N * M /* tx_data */ + 64 /* mbarriers */ + 8 * N * 2 + 64;
   }
 };
@@ -193,18 +193,13 @@ __device__ __forceinline__ void task_load(TaskRegs<N> &t, const WarpCtx &c, int 
 
 // demap of one equalised symbol: returns the symbol index, writes 2*MB LLRs
 template <int MB>
-__device__ __forceinline__ unsigned demap_one(cf z, float isig, const float *refs, const float2 *lut, float *llr,
+__device__ __forceinline__ unsigned demap_one(cf z, float isig, const float *refs, const DemapConst &dc, float *llr,
                                               bool want_llr) {
-  constexpr int PL = 1 << MB;
   const unsigned si = slice_axis_refs<MB>(z.x, refs), sq = slice_axis_refs<MB>(z.y, refs);
   if (want_llr) {
-    const float2 *li = lut + si, *lq = lut + sq;
-#pragma unroll
-    for (int b = 0; b < MB; b++) {
-      const float2 ci = li[b * PL], cq = lq[b * PL];
-      llr[b] = fmaf(ci.x, z.x, ci.y) * isig;
-      llr[MB + b] = fmaf(cq.x, z.y, cq.y) * isig;
-    }
+    const float k = dc.k4 * isig;
+    llr_axis<MB>(z.x, k, dc, llr);
+    llr_axis<MB>(z.y, k, dc, llr + MB);
   }
   // (gray(si) << MB) | gray(sq) in one pass: the shifted-in bit that crosses from si into sq's
   // top position is masked off
@@ -214,7 +209,7 @@ __device__ __forceinline__ unsigned demap_one(cf z, float isig, const float *ref
 
 template <int N, int MB>
 __device__ __forceinline__ void task_compute(const TaskRegs<N> &t, const ChainArgs &a, const float4 *y4,
-                                             long long o, float *lp, unsigned char *bp, const float2 *lut,
+                                             long long o, float *lp, unsigned char *bp, const DemapConst &lut,
                                              const float *refs, unsigned long long pol_stream,
                                              unsigned txv, unsigned *cnt_s) {
   constexpr int Q = 2 * MB;
@@ -317,7 +312,7 @@ __device__ __forceinline__ void flush_counts(const unsigned *eb, const unsigned 
 template <int LOG2M, int N, int MB>
 __device__ __forceinline__ void detect_symbol(const FusedArgs &fa, TaskRegs<N> &cur, const WarpCtx &wc,
                                               const cf *buf, const unsigned char *txs, long long symbase,
-                                              const float2 *lut,
+                                              const DemapConst &lut,
                                               const float *refs, unsigned long long pol_keep,
                                               unsigned long long pol_stream, unsigned *cnt) {
   using TR = FusedTraits<LOG2M, N>;
@@ -365,7 +360,7 @@ __device__ __forceinline__ void detect_symbol(const FusedArgs &fa, TaskRegs<N> &
 }
 
 template <int LOG2M, int N>
-__global__ void __launch_bounds__(FusedTraits<LOG2M, N>::THREADS, FusedTraits<LOG2M, N>::MIN_CTAS) k_rx_fused(FusedArgs fa, DemapLut lutp) {
+__global__ void __launch_bounds__(FusedTraits<LOG2M, N>::THREADS, FusedTraits<LOG2M, N>::MIN_CTAS) k_rx_fused(FusedArgs fa, DemapConst lutp) {
   using TR = FusedTraits<LOG2M, N>;
   using FF = Fft<LOG2M>;
   using PL = FftPlan<LOG2M>;
@@ -377,8 +372,7 @@ __global__ void __launch_bounds__(FusedTraits<LOG2M, N>::THREADS, FusedTraits<LO
   cf *buf1 = buf0 + TR::BUF_ELEMS;
   unsigned char *stage_base = reinterpret_cast<unsigned char *>(buf1 + TR::BUF_ELEMS);
   const int stage_stride = fa.llr_stage_bytes + 64;  // llr block followed by 64 B of packed bits
-  float2 *lut = reinterpret_cast<float2 *>(stage_base + (size_t)NWARPS * 2 * stage_stride);
-  cf *tw_s = reinterpret_cast<cf *>(lut + 64);  // stage twiddles, copied once
+  cf *tw_s = reinterpret_cast<cf *>(stage_base + (size_t)NWARPS * 2 * stage_stride);  // stage twiddles, copied once
   unsigned char *txbuf = reinterpret_cast<unsigned char *>(tw_s + TR::TW_SMEM_ELEMS);  // [2][N][M] tx symbols
   unsigned long long *mbar = reinterpret_cast<unsigned long long *>(txbuf + 2 * N * M);  // full[2], empty[2]
   unsigned *cnt = reinterpret_cast<unsigned *>(mbar + 4);  // [N][2] bit errors, symbol errors
@@ -390,7 +384,6 @@ __global__ void __launch_bounds__(FusedTraits<LOG2M, N>::THREADS, FusedTraits<LO
   const int q = a.q;
   const unsigned long long pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
 
-  if (tid < 64) lut[tid] = make_float2(lutp.slope[tid], lutp.icpt[tid]);
   for (int i = tid; i < TR::TW_SMEM_ELEMS; i += THREADS) tw_s[i] = a.tw[i];
   const cf *tws = TR::TW_SMEM ? tw_s : a.tw;
   if (tid < 2 * N) cnt[tid] = 0;
@@ -552,7 +545,7 @@ __global__ void __launch_bounds__(FusedTraits<LOG2M, N>::THREADS, FusedTraits<LO
       }
     } else {
       // ---------------- detect + demap + count ----------------
-#define DETECT(MBV) detect_symbol<LOG2M, N, MBV>(fa, cur, wc, buf, txbuf + (g & 1) * N * M, symbase, lut, refs, pol_keep, pol_stream, cnt)
+#define DETECT(MBV) detect_symbol<LOG2M, N, MBV>(fa, cur, wc, buf, txbuf + (g & 1) * N * M, symbase, lutp, refs, pol_keep, pol_stream, cnt)
       switch (q) {
         case 2: DETECT(1); break;
         case 4: DETECT(2); break;
@@ -587,14 +580,12 @@ __global__ void __launch_bounds__(FusedTraits<LOG2M, N>::THREADS, FusedTraits<LO
 // W/gain/isig/tx loads of the next half-task are in flight while the current one is computed.
 // LLRs and packed bits are staged per warp in their final byte order and leave by TMA bulk store.
 template <int N, int MB>
-__global__ void __launch_bounds__(256, (N <= 4 ? 3 : 2)) k_detect_lean(ChainArgs a, DemapLut lutp, int llr_stage_bytes) {
-  constexpr int Q = 2 * MB, PL = 1 << MB, WARPS = 8;
+__global__ void __launch_bounds__(256, (N <= 4 ? 3 : 2)) k_detect_lean(ChainArgs a, DemapConst lutp, int llr_stage_bytes) {
+  constexpr int Q = 2 * MB, WARPS = 8;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ float2 lut[64];
   __shared__ unsigned cnt[2 * N];
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  if (tid < 64) lut[tid] = make_float2(lutp.slope[tid], lutp.icpt[tid]);
   if (tid < 2 * N) cnt[tid] = 0;
   __syncthreads();
   const int M = a.M;
@@ -658,15 +649,11 @@ __global__ void __launch_bounds__(256, (N <= 4 ? 3 : 2)) k_detect_lean(ChainArgs
       if (a.eq) st_hint2(a.eq + o, make_float2(z.x, z.y), pol_stream);
       if (a.rx_data) a.rx_data[o] = (unsigned char)symh[h];
       if (want_llr) {
-        const float2 *li = lut + si, *lq = lut + sq;
         float2 *lp = reinterpret_cast<float2 *>(slot) + (32 * h + lane) * MB;
         float l[Q];
-#pragma unroll
-        for (int b = 0; b < MB; b++) {
-          const float2 ci = li[b * PL], cq = lq[b * PL];
-          l[b] = fmaf(ci.x, z.x, ci.y) * cur.is;
-          l[MB + b] = fmaf(cq.x, z.y, cq.y) * cur.is;
-        }
+        const float kk = lutp.k4 * cur.is;
+        llr_axis<MB>(z.x, kk, lutp, l);
+        llr_axis<MB>(z.y, kk, lutp, l + MB);
 #pragma unroll
         for (int b = 0; b < MB; b++) lp[b] = make_float2(l[2 * b], l[2 * b + 1]);
       }

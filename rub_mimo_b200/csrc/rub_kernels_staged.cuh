@@ -192,8 +192,8 @@ __global__ void k_weights(ChainArgs a, WeightMode wm) {
 // blockIdx.x = (frame, symbol, stream); each thread owns 8 consecutive occupied carriers so
 // its packed hard bits are whole bytes for every modulation.
 template <int N>
-__global__ void __launch_bounds__(128) k_detect(ChainArgs a, DemapLut lutp) {
-  __shared__ DemapLut lut;
+__global__ void __launch_bounds__(128) k_detect(ChainArgs a, DemapConst lutp) {
+  __shared__ DemapConst lut;
   __shared__ unsigned long long red[3];
   if (threadIdx.x == 0) { lut = lutp; red[0] = red[1] = red[2] = 0; }
   __syncthreads();
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(128) k_detect(ChainArgs a, DemapLut lutp) {
   const int d = (blockIdx.x / N) % a.D;
   const long long frame = blockIdx.x / (N * a.D);
   const int jg = blockIdx.y * blockDim.x + threadIdx.x;
-  const int m = lut.m, q = a.q, PL = 1 << m;
+  const int m = lut.m, q = a.q;
   const float alpha = lut.alpha;
   const long long nsym = a.T + a.D;
   const cf *Yf = a.Y + ((frame * nsym + a.T + d) * N) * a.M;
@@ -227,10 +227,11 @@ __global__ void __launch_bounds__(128) k_detect(ChainArgs a, DemapLut lutp) {
     if (a.llr) {
       const float is = sf[k];
       float *lp = a.llr + o * q;
-      for (int b = 0; b < m; b++) {
-        lp[b] = fmaf(lut.slope[b * PL + si], z.x, lut.icpt[b * PL + si]) * is;
-        lp[m + b] = fmaf(lut.slope[b * PL + sq], z.y, lut.icpt[b * PL + sq]) * is;
-      }
+      float l[8];
+      const float kk = lut.k4 * is;
+      llr_axis_rt(z.x, kk, m, lut, l);
+      llr_axis_rt(z.y, kk, m, lut, l + m);
+      for (int b = 0; b < 2 * m; b++) lp[b] = l[b];
     }
     word = (word << q) | sym;
     ns++;

@@ -12,7 +12,6 @@
 
 #include "rub_internal.h"
 #include "rub_kernels_fused.cuh"
-#include "rub_kernels_fused32.cuh"
 #include "rub_kernels_staged.cuh"
 #include "rub_kernels_sync.cuh"
 #include "rub_kernels_tx.cuh"
@@ -77,7 +76,7 @@ struct rub_rx {
   void *d_sync = nullptr;  // grow-only scratch of the synchronisation calls
   size_t sync_bytes = 0;
   unsigned char *d_null = nullptr;
-  DemapLut lut;
+  DemapConst lut;
   WeightMode wm;
   // staged scratch
   void *d_scratch = nullptr;
@@ -86,7 +85,6 @@ struct rub_rx {
   cf *d_fW = nullptr;
   float *d_fG = nullptr;
   int fused_grid = 0;
-  bool fused32 = false;  // 32-warp variant of the fused kernel (rub_kernels_fused32.cuh)
   size_t fused_smem = 0;
   bool fused_ready = false;
   uint64_t *d_counters = nullptr;
@@ -117,24 +115,9 @@ static rub_status fused_prepare(rub_rx *h, size_t *smem_out, int *grid_out) {
   return RUB_OK;
 }
 template <int LOG2M, int N>
-static void fused_launch(int grid, size_t smem, cudaStream_t st, const FusedArgs &fa, const DemapLut &lut) {
+static void fused_launch(int grid, size_t smem, cudaStream_t st, const FusedArgs &fa, const DemapConst &lut) {
   k_rx_fused<LOG2M, N><<<grid, FusedTraits<LOG2M, N>::THREADS, smem, st>>>(fa, lut);
 }
-
-template <int LOG2M, int N>
-static rub_status fused32_prepare(rub_rx *h, size_t *smem_out, int *grid_out) {
-  using TR = Fused32Traits<LOG2M, N>;
-  const size_t smem = TR::smem_bytes((int)h->h.q);
-  CUDA_TRY(cudaFuncSetAttribute(k_rx_fused32<LOG2M, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int occ = 0;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_rx_fused32<LOG2M, N>, TR::THREADS, smem));
-  if (occ < 1) { set_error("fused32 kernel does not fit (smem %zu B)", smem); return RUB_ERR_UNSUPPORTED; }
-  *smem_out = smem;
-  *grid_out = occ * h->num_sms;
-  return RUB_OK;
-}
-// the 32-warp variant exists for the configurations where it wins
-static bool fused32_has_instance(uint32_t l2, uint32_t N) { return l2 == 11 && N == 4; }
 
 // the (log2 M, N) pairs the fused kernel is instantiated for
 #define RUB_FUSED_LIST(X) X(9, 2) X(9, 4) X(10, 2) X(10, 4) X(11, 1) X(11, 2) X(11, 4) X(12, 1) X(12, 2)
@@ -146,14 +129,12 @@ static bool fused_has_instance(uint32_t l2, uint32_t N) {
   return false;
 }
 static rub_status fused_prepare_dispatch(rub_rx *h, size_t *smem, int *grid) {
-  if (h->fused32) return fused32_prepare<11, 4>(h, smem, grid);
 #define X(L, NN) if (h->h.log2M == L && h->h.N == NN) return fused_prepare<L, NN>(h, smem, grid);
   RUB_FUSED_LIST(X)
 #undef X
   return RUB_ERR_UNSUPPORTED;
 }
 static void fused_launch_dispatch(rub_rx *h, int grid, size_t smem, const FusedArgs &fa) {
-  if (h->fused32) { k_rx_fused32<11, 4><<<grid, Fused32Traits<11, 4>::THREADS, smem, h->stream>>>(fa, h->lut); return; }
 #define X(L, NN) if (h->h.log2M == L && h->h.N == NN) { fused_launch<L, NN>(grid, smem, h->stream, fa, h->lut); return; }
   RUB_FUSED_LIST(X)
 #undef X
@@ -254,7 +235,7 @@ extern "C" rub_status rub_rx_create(rub_rx **out, const rub_config *cfg, const f
     CT(cudaMalloc(&h->d_s1, sizeof(cf) * s1t.size()));
     CT(cudaMemcpy(h->d_s1, s1t.data(), sizeof(cf) * s1t.size(), cudaMemcpyHostToDevice));
   }
-  build_demap_lut(c.q, h->lut);
+  build_demap_const(c.q, h->lut);
   fill_weight_mode(h);
   CT(cudaMalloc(&h->d_counters, sizeof(uint64_t) * 4 * 8));
   CT(cudaMemset(h->d_counters, 0, sizeof(uint64_t) * 4 * 8));
@@ -279,7 +260,7 @@ extern "C" void rub_rx_destroy(rub_rx *h) {
 }
 
 extern "C" rub_status rub_rx_set_path(rub_rx *h, uint32_t path) {
-  if (!h || path > RUB_PATH_FUSED32) return RUB_ERR_INVALID_ARG;
+  if (!h || path > RUB_PATH_FUSED) return RUB_ERR_INVALID_ARG;
   h->path = path;
   return RUB_OK;
 }
@@ -463,15 +444,7 @@ static rub_status run_staged(rub_rx *h, ChainArgs a, const rub_rx_io *io, uint32
 
 static rub_status run_fused(rub_rx *h, const ChainArgs &a, uint32_t n_frames, bool timed) {
   const HostCfg &c = h->h;
-  const bool want32 = h->path == RUB_PATH_FUSED32;
-  if (h->fused_ready && h->fused32 != want32) {  // the variant changed: shared-memory size and grid are per kernel
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
-    cudaFree(h->d_fW); cudaFree(h->d_fG);
-    h->d_fW = nullptr; h->d_fG = nullptr;
-    h->fused_ready = false;
-  }
   if (!h->fused_ready) {
-    h->fused32 = want32;
     int grid = 0;
     size_t smem = 0;
     rub_status st = fused_prepare_dispatch(h, &smem, &grid);
@@ -496,7 +469,7 @@ static rub_status run_fused(rub_rx *h, const ChainArgs &a, uint32_t n_frames, bo
   if (timed) cudaEventRecord(h->ev[3], h->stream);
   h->launches += 1;
   CUDA_TRY(cudaGetLastError());
-  h->last_path = want32 ? RUB_PATH_FUSED32 : RUB_PATH_FUSED;
+  h->last_path = RUB_PATH_FUSED;
   return RUB_OK;
 }
 
@@ -532,8 +505,8 @@ static rub_status process_device(rub_rx *h, const rub_rx_io *io, uint32_t n_fram
     return RUB_ERR_INVALID_ARG;
   }
   const bool can_fuse = fused_eligible(h, io, frame_stride, rx_stride);
-  const bool req_fused = h->path == RUB_PATH_FUSED || h->path == RUB_PATH_FUSED32;
-  if (req_fused && (!can_fuse || (h->path == RUB_PATH_FUSED32 && !fused32_has_instance(h->h.log2M, h->h.N)))) {
+  const bool req_fused = h->path == RUB_PATH_FUSED;
+  if (req_fused && !can_fuse) {
     set_error("fused path requested but the configuration / buffers are not eligible");
     return RUB_ERR_UNSUPPORTED;
   }

@@ -61,20 +61,6 @@ def test_fused_path_matches_oracle(name):
     assert got["path"] == rub.PATH_FUSED
 
 
-@pytest.mark.parametrize("name", ["c3_small", "c3_biased_zf"])
-def test_fused32_variant_matches_oracle(name):
-    """The opt-in 32-warp fused kernel (rub_kernels_fused32.cuh, 4x4 / 2048) is bit-exact too."""
-    got = _run(name, rub.PATH_FUSED32)
-    assert got["path"] == rub.PATH_FUSED32
-
-
-def test_fused32_is_refused_where_it_has_no_instance():
-    kw, nf, sk = CASES["c2_small"]
-    cfg, S1, iq, tx = make_case(rub.Config(**kw), 2, seed=3, **sk)
-    with pytest.raises(rub.RubError):
-        gpu_run(cfg, S1, iq, tx, path=rub.PATH_FUSED32)
-
-
 def test_ragged_allocation_uses_staged_path():
     p = rub.ofdmframe_init_default_sctype(512, use_all_carriers=False, add_null_carriers=True)
     cfg = rub.Config(M=512, cp_len=36, num_streams=2, num_access_codes=2, num_data_symbols=5,

@@ -22,7 +22,7 @@ for i in range(8):
     rx.process_batch(d_iq, out=out, out_mask=rub.OUT_EQ | rub.OUT_LLR | rub.OUT_BITS, tx_data=d_tx)
     rx.sync()
     ts.append(rx.last_timing()[0])
-path = {1: "staged", 2: "fused", 3: "fused32"}[rx.last_path]
+path = {1: "staged", 2: "fused"}[rx.last_path]
 b = rx.algorithmic_bytes(F, rub.OUT_EQ | rub.OUT_LLR | rub.OUT_BITS, True) if hasattr(rx, "algorithmic_bytes") else 0
 print(f"{M}/{cp} {N}x{N} nac{nac} D{D} q{q} F{F} {path}: {min(ts[2:]):.4f} ms  ({b / min(ts[2:]) / 1e6:.0f} GB/s)")
 rx.close()
