@@ -208,7 +208,13 @@ rub_status rub_rx_set_S0(rub_rx *h, const float *s0);
 rub_status rub_comm_get_unique_id(uint8_t id[RUB_NCCL_UNIQUE_ID_BYTES]);
 rub_status rub_comm_init(rub_rx *h, const uint8_t id[RUB_NCCL_UNIQUE_ID_BYTES], int rank,
                          int world_size);
-rub_status rub_allreduce_counters(rub_rx *h); /* in place on the handle's counters      */
+/* Global counters = sum over ranks of each rank's cumulative local counters (the handle's own
+ * counters are only read, so the call is idempotent and may follow every batch).  The local
+ * counters are snapshotted on the handle's stream and reduced on a side stream: the next batch
+ * does not wait for the collective.  With world_size 1 (no rub_comm_init) the result equals the
+ * local counters.  rub_rx_read_counters_global waits for the latest reduction and copies it out. */
+rub_status rub_allreduce_counters(rub_rx *h);
+rub_status rub_rx_read_counters_global(rub_rx *h, uint64_t *host_out /* [4*N] */);
 rub_status rub_comm_destroy(rub_rx *h);
 /* frame range [begin, end) of `rank` when n_frames are sharded over world_size ranks    */
 void rub_shard_range(uint64_t n_frames, int rank, int world_size, uint64_t *begin,

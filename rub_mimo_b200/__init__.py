@@ -109,7 +109,7 @@ ABI_SYMBOLS = [
     "rub_rx_device_counters", "rub_rx_read_counters", "rub_rx_launch_count", "rub_rx_last_timing",
     "rub_rx_algorithmic_bytes", "rub_rx_sc_metric", "rub_rx_timing_search", "rub_rx_set_S0",
     "rub_framegen_batch_device", "rub_rx_process_files", "rub_config_from_args", "rub_config_from_json", "rub_rx_process_capture",
-    "rub_comm_get_unique_id", "rub_comm_init", "rub_allreduce_counters",
+    "rub_comm_get_unique_id", "rub_comm_init", "rub_allreduce_counters", "rub_rx_read_counters_global",
     "rub_comm_destroy", "rub_shard_range", "rub_msequence_init", "rub_msequence_reset",
     "rub_msequence_advance", "rub_msequence_generate_symbol", "rub_ofdmframe_init_default_sctype",
     "rub_ofdmframe_validate_sctype", "rub_ofdmframe_init_S0", "rub_ofdmframe_init_S1",
@@ -170,6 +170,8 @@ def lib():
         L.rub_rx_launch_count.argtypes = [C.c_void_p]
         L.rub_rx_device_counters.argtypes = [C.c_void_p]
         L.rub_rx_read_counters.argtypes = [C.c_void_p, C.c_void_p]
+        L.rub_rx_read_counters_global.argtypes = [C.c_void_p, C.c_void_p]
+        L.rub_rx_read_counters_global.restype = C.c_int
         L.rub_rx_last_timing.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.rub_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.rub_rx_sc_metric.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
@@ -678,7 +680,14 @@ class Receiver:
         _check(lib().rub_comm_init(self.h, buf, rank, world_size))
 
     def allreduce_counters(self):
+        """Snapshot the local cumulative counters and all-reduce them on a side stream (idempotent)."""
         _check(lib().rub_allreduce_counters(self.h))
+
+    def read_counters_global(self):
+        """[N][4] uint64: the latest all-reduced counters (sum over ranks)."""
+        out = np.zeros((self.cfg.N, 4), np.uint64)
+        _check(lib().rub_rx_read_counters_global(self.h, _p(out)))
+        return out
 
 
 def comm_get_unique_id():

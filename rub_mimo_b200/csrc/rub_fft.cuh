@@ -98,6 +98,28 @@ struct FftStage {
       bfly<R>(v + b * R);
     }
   }
+  // The stage twiddles of thread `tid` depend on tid only, so a persistent thread can keep them
+  // in registers: tw[b*(R-1) + t-1] = tws[(t-1)*NS + (tid + b*NT) % NS]
+  static constexpr int NTW = (NS > 1) ? B * (R - 1) : 0;
+  RUB_HD static void load_twiddles(int tid, const cf *tws, cf *tw) {
+#pragma unroll
+    for (int b = 0; b < B; b++) {
+      const int k = (tid + b * NT) % NS;
+#pragma unroll
+      for (int t = 1; t < R; t++) tw[b * (R - 1) + t - 1] = tws[(t - 1) * NS + k];
+    }
+  }
+  // same arithmetic as compute(), twiddles taken from the caller's registers
+  RUB_HD static void compute_pre(cf *v, const cf *tw) {
+#pragma unroll
+    for (int b = 0; b < B; b++) {
+      if (NS > 1) {
+#pragma unroll
+        for (int t = 1; t < R; t++) v[b * R + t] = cmul(v[b * R + t], tw[b * (R - 1) + t - 1]);
+      }
+      bfly<R>(v + b * R);
+    }
+  }
   template <bool PAD_OUT, bool SCALE>
   RUB_HD static void store(int tid, const cf *v, cf *out, float scale) {
 #pragma unroll

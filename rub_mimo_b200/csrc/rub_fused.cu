@@ -1,0 +1,68 @@
+// rub_fused.cu — instances and host launchers of the monolithic fused kernel and of the
+// block-mapped detect kernel (rub_kernels_fused.cuh).
+#include "rub_kernels_fused.cuh"
+#include "rub_launch.h"
+
+namespace rub {
+
+// the (log2 M, N) pairs the fused kernel is instantiated for
+#define RUB_FUSED_LIST(X) X(9, 2) X(9, 4) X(10, 2) X(10, 4) X(11, 1) X(11, 2) X(11, 4) X(12, 1) X(12, 2)
+
+bool fused_has_instance(uint32_t l2, uint32_t N) {
+#define X(L, NN) if (l2 == L && N == NN) return true;
+  RUB_FUSED_LIST(X)
+#undef X
+  return false;
+}
+template <int LOG2M, int N>
+static cudaError_t prepare(uint32_t q, size_t *smem_out, int *occ) {
+  using TR = FusedTraits<LOG2M, N>;
+  const size_t smem = TR::smem_bytes((int)q);
+  cudaError_t e = cudaFuncSetAttribute(k_rx_fused<LOG2M, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  *smem_out = smem;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_rx_fused<LOG2M, N>, TR::THREADS, smem);
+}
+cudaError_t fused_prepare(uint32_t l2, uint32_t N, uint32_t q, size_t *smem, int *occ) {
+#define X(L, NN) if (l2 == L && N == NN) return prepare<L, NN>(q, smem, occ);
+  RUB_FUSED_LIST(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
+void fused_launch(uint32_t l2, uint32_t N, int grid, size_t smem, cudaStream_t st, const FusedArgs &fa, const DemapConst &dc) {
+#define X(L, NN) if (l2 == L && N == NN) { k_rx_fused<L, NN><<<grid, FusedTraits<L, NN>::THREADS, smem, st>>>(fa, dc); return; }
+  RUB_FUSED_LIST(X)
+#undef X
+}
+
+// block-mapped detect kernel: all carriers occupied, 16-byte aligned outputs, N in {1,2,4,8}
+template <int N, int MB>
+static void launch_lean(const ChainArgs &a, const DemapConst &dc, cudaStream_t st) {
+  const int llr_stage = 256 * 2 * MB;
+  const size_t smem = (size_t)8 * 2 * (llr_stage + 64);  // 8 warps x 2 staging slots
+  const long long nwork = (long long)a.n_frames * a.D * (a.M / 64);
+  k_detect_lean<N, MB><<<(unsigned)((nwork + 7) / 8), 256, smem, st>>>(a, dc, llr_stage);
+}
+template <int N>
+static void launch_lean_q(const ChainArgs &a, const DemapConst &dc, cudaStream_t st) {
+  switch (a.q) {
+    case 2: launch_lean<N, 1>(a, dc, st); break;
+    case 4: launch_lean<N, 2>(a, dc, st); break;
+    case 6: launch_lean<N, 3>(a, dc, st); break;
+    default: launch_lean<N, 4>(a, dc, st); break;
+  }
+}
+bool detect_lean_launch(const ChainArgs &a, const DemapConst &dc, cudaStream_t st) {
+  if (a.Mo != a.M || (a.M % 64)) return false;
+  if (((uintptr_t)a.llr & 15) || ((uintptr_t)a.bits & 15) || ((uintptr_t)a.eq & 15)) return false;
+  if (((uintptr_t)a.rx_data & 1) || ((uintptr_t)a.tx_data & 1)) return false;
+  switch (a.N) {
+    case 1: launch_lean_q<1>(a, dc, st); return true;
+    case 2: launch_lean_q<2>(a, dc, st); return true;
+    case 4: launch_lean_q<4>(a, dc, st); return true;
+    case 8: launch_lean_q<8>(a, dc, st); return true;
+    default: return false;
+  }
+}
+
+}  // namespace rub

@@ -21,17 +21,10 @@
 #pragma once
 #include <cuda_runtime.h>
 
-#include "rub_kernels_staged.cuh"
+#include "rub_internal.h"
+#include "rub_kernels_args.cuh"
 
 namespace rub {
-
-struct FusedArgs {
-  ChainArgs a;
-  cf *scratchW;      // [grid][N*N][M]   (G accumulates here, then W in place)
-  float *scratchG;   // [grid][2][N][M]  gain, isig
-  int llr_stage_bytes;  // 256*q
-  WeightMode wm;
-};
 
 // ---------------------------------------------------------------- PTX helpers ---------
 __device__ __forceinline__ unsigned smem_u32(const void *p) {

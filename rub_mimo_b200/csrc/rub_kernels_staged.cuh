@@ -6,38 +6,9 @@
 #include <cuda_runtime.h>
 
 #include "rub_internal.h"
+#include "rub_kernels_args.cuh"
 
 namespace rub {
-
-struct ChainArgs {
-  // input
-  const cf *iq;
-  unsigned long long frame_stride, rx_stride, first_sample;
-  const int *timing;         // [frame][rx][T] or null
-  const int *payload_start;  // [frame] or null
-  // geometry
-  int M, cp, L, N, nac, D, T, Mo, q, P, n_frames, row_bytes;
-  float dn, s_ls;
-  unsigned flags;
-  int estimator;
-  // tables
-  const cf *tw;            // packed stage twiddles
-  const unsigned short *occ;  // j -> k
-  const float *sgn;        // [tx][code][k] in {-1,0,+1}
-  const unsigned char *scnull;  // [k] 1 = null carrier
-  // scratch / outputs
-  cf *Y;       // [frame][sym][rx][k]
-  cf *G;       // [frame][rx][tx][k]
-  cf *W;       // [frame][stream][rx][k]
-  float *gain; // [frame][stream][k]
-  float *isig; // [frame][stream][k]
-  cf *eq;
-  float *llr;
-  unsigned char *bits;
-  unsigned char *rx_data;
-  const unsigned char *tx_data;
-  unsigned long long *counters;
-};
 
 __device__ __forceinline__ long long window_start(const ChainArgs &a, int frame, int r, int sym) {
   if (sym < a.T) {

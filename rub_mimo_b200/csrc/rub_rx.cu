@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -11,7 +12,7 @@
 #include <vector>
 
 #include "rub_internal.h"
-#include "rub_kernels_fused.cuh"
+#include "rub_launch.h"
 #include "rub_kernels_staged.cuh"
 #include "rub_kernels_sync.cuh"
 #include "rub_kernels_tx.cuh"
@@ -85,8 +86,10 @@ struct rub_rx {
   cf *d_fW = nullptr;
   float *d_fG = nullptr;
   int fused_grid = 0;
+  bool ws = false;  // the warp-specialised fused kernel (rub_kernels_ws.cuh) serves this configuration
   size_t fused_smem = 0;
   bool fused_ready = false;
+  bool fused_unfit = false;  // no fused kernel fits this configuration (shared memory): staged path
   uint64_t *d_counters = nullptr;
   uint32_t path = RUB_PATH_AUTO, last_path = 0;
   uint64_t launches = 0;
@@ -97,47 +100,37 @@ struct rub_rx {
   void *d_pipe = nullptr;
   size_t pipe_bytes = 0;
   cudaEvent_t pev[12] = {};
-  // comm
+  // comm: the counter all-reduce runs on its own stream against double-buffered snapshots
   void *comm = nullptr;
   int rank = 0, world = 1;
+  cudaStream_t s_comm = nullptr;
+  uint64_t *d_snap = nullptr;    // [2][32] snapshot of d_counters | [2][32] reduced result
+  cudaEvent_t cev[4] = {};       // snapshot taken [2], reduction done [2]
+  uint32_t n_reduce = 0;         // reductions issued so far
 };
 
-template <int LOG2M, int N>
-static rub_status fused_prepare(rub_rx *h, size_t *smem_out, int *grid_out) {
-  using TR = FusedTraits<LOG2M, N>;
-  const size_t smem = TR::smem_bytes((int)h->h.q);
-  CUDA_TRY(cudaFuncSetAttribute(k_rx_fused<LOG2M, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+// fused kernels live in their own translation units (rub_fused.cu, rub_ws.cu)
+static rub_status fused_prepare_dispatch(rub_rx *h, size_t *smem, int *grid) {
+  const char *e = getenv("RUB_FUSED_WS");  // development switch: RUB_FUSED_WS=1 selects the warp-specialised kernel
+  h->ws = (e && e[0] == '1') && ws_has_instance(h->h.log2M, h->h.N);
   int occ = 0;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_rx_fused<LOG2M, N>, TR::THREADS, smem));
-  if (occ < 1) { set_error("fused kernel does not fit (smem %zu B)", smem); return RUB_ERR_UNSUPPORTED; }
-  *smem_out = smem;
-  *grid_out = occ * h->num_sms;
+  cudaError_t ce = cudaErrorInvalidValue;
+  if (h->ws) {
+    ce = ws_prepare(h->h.log2M, h->h.N, h->h.q, smem, &occ);
+    if (ce != cudaSuccess || occ < 1) { cudaGetLastError(); h->ws = false; }  // e.g. 256-QAM staging does not fit: monolithic kernel
+  }
+  if (!h->ws) ce = fused_prepare(h->h.log2M, h->h.N, h->h.q, smem, &occ);
+  if (ce != cudaSuccess || occ < 1) {
+    cudaGetLastError();
+    set_error("no fused kernel fits this configuration (shared memory %zu B)", *smem);
+    return RUB_ERR_UNSUPPORTED;
+  }
+  *grid = (h->ws ? 1 : occ) * h->num_sms;
   return RUB_OK;
 }
-template <int LOG2M, int N>
-static void fused_launch(int grid, size_t smem, cudaStream_t st, const FusedArgs &fa, const DemapConst &lut) {
-  k_rx_fused<LOG2M, N><<<grid, FusedTraits<LOG2M, N>::THREADS, smem, st>>>(fa, lut);
-}
-
-// the (log2 M, N) pairs the fused kernel is instantiated for
-#define RUB_FUSED_LIST(X) X(9, 2) X(9, 4) X(10, 2) X(10, 4) X(11, 1) X(11, 2) X(11, 4) X(12, 1) X(12, 2)
-
-static bool fused_has_instance(uint32_t l2, uint32_t N) {
-#define X(L, NN) if (l2 == L && N == NN) return true;
-  RUB_FUSED_LIST(X)
-#undef X
-  return false;
-}
-static rub_status fused_prepare_dispatch(rub_rx *h, size_t *smem, int *grid) {
-#define X(L, NN) if (h->h.log2M == L && h->h.N == NN) return fused_prepare<L, NN>(h, smem, grid);
-  RUB_FUSED_LIST(X)
-#undef X
-  return RUB_ERR_UNSUPPORTED;
-}
 static void fused_launch_dispatch(rub_rx *h, int grid, size_t smem, const FusedArgs &fa) {
-#define X(L, NN) if (h->h.log2M == L && h->h.N == NN) { fused_launch<L, NN>(grid, smem, h->stream, fa, h->lut); return; }
-  RUB_FUSED_LIST(X)
-#undef X
+  if (h->ws) ws_launch(h->h.log2M, h->h.N, grid, smem, h->stream, fa, h->lut);
+  else fused_launch(h->h.log2M, h->h.N, grid, smem, h->stream, fa, h->lut);
 }
 
 // is the fused kernel applicable to this configuration + call?
@@ -248,11 +241,15 @@ extern "C" void rub_rx_destroy(rub_rx *h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->s_comm) cudaStreamSynchronize(h->s_comm);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   cudaFree(h->d_tw); cudaFree(h->d_occ); cudaFree(h->d_sgn); cudaFree(h->d_null); cudaFree(h->d_s1); cudaFree(h->d_s0); cudaFree(h->d_sync);
   cudaFree(h->d_scratch); cudaFree(h->d_fW); cudaFree(h->d_fG); cudaFree(h->d_counters); cudaFree(h->d_pipe);
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);
   for (auto &e : h->pev) if (e) cudaEventDestroy(e);
+  cudaFree(h->d_snap);
+  for (auto &e : h->cev) if (e) cudaEventDestroy(e);
+  if (h->s_comm) cudaStreamDestroy(h->s_comm);
   if (h->s_in) cudaStreamDestroy(h->s_in);
   if (h->s_out) cudaStreamDestroy(h->s_out);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -329,37 +326,14 @@ static void launch_fft(const ChainArgs &a, cudaStream_t st, cudaError_t *err) {
   const unsigned grid = (unsigned)((total + F - 1) / F);
   k_fft_staged<LOG2M, F><<<grid, NT * F, smem, st>>>(a);
 }
-template <int N, int MB>
-static void launch_detect_lean(const ChainArgs &a, const rub_rx *h, cudaStream_t st) {
-  const int llr_stage = 256 * 2 * MB;
-  const size_t smem = (size_t)8 * 2 * (llr_stage + 64);  // 8 warps x 2 staging slots
-  const long long nwork = (long long)a.n_frames * a.D * (a.M / 64);
-  k_detect_lean<N, MB><<<(unsigned)((nwork + 7) / 8), 256, smem, st>>>(a, h->lut, llr_stage);
-}
-// block-mapped detect kernel: all carriers occupied, 16-byte aligned outputs, N in {1,2,4,8}
-static bool detect_lean_ok(const ChainArgs &a) {
-  if (a.Mo != a.M || (a.M % 64)) return false;
-  if (!(a.N == 1 || a.N == 2 || a.N == 4 || a.N == 8)) return false;
-  if (((uintptr_t)a.llr & 15) || ((uintptr_t)a.bits & 15) || ((uintptr_t)a.eq & 15)) return false;
-  if (((uintptr_t)a.rx_data & 1) || ((uintptr_t)a.tx_data & 1)) return false;
-  return true;
-}
 template <int N>
 static void launch_weights_detect(const ChainArgs &a, const rub_rx *h, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1) {
   const long long tw = (long long)a.n_frames * a.M;
   k_weights<N><<<(unsigned)((tw + 127) / 128), 128, 0, st>>>(a, h->wm);
   if (e0) cudaEventRecord(e0, st);
-  if constexpr (N == 1 || N == 2 || N == 4 || N == 8) {
-    if (detect_lean_ok(a)) {
-      switch (a.q) {
-        case 2: launch_detect_lean<N, 1>(a, h, st); break;
-        case 4: launch_detect_lean<N, 2>(a, h, st); break;
-        case 6: launch_detect_lean<N, 3>(a, h, st); break;
-        default: launch_detect_lean<N, 4>(a, h, st); break;
-      }
-      if (e1) cudaEventRecord(e1, st);
-      return;
-    }
+  if (detect_lean_launch(a, h->lut, st)) {
+    if (e1) cudaEventRecord(e1, st);
+    return;
   }
   const int groups = (a.Mo + 7) / 8;
   dim3 grid((unsigned)((long long)a.n_frames * a.D * N), (unsigned)((groups + 127) / 128));
@@ -448,7 +422,7 @@ static rub_status run_fused(rub_rx *h, const ChainArgs &a, uint32_t n_frames, bo
     int grid = 0;
     size_t smem = 0;
     rub_status st = fused_prepare_dispatch(h, &smem, &grid);
-    if (st) return st;
+    if (st) { h->fused_unfit = st == RUB_ERR_UNSUPPORTED; return st; }
     h->fused_grid = grid;
     h->fused_smem = smem;
     CUDA_TRY(cudaMalloc(&h->d_fW, (size_t)grid * c.N * c.N * c.M * sizeof(cf)));
@@ -506,13 +480,15 @@ static rub_status process_device(rub_rx *h, const rub_rx_io *io, uint32_t n_fram
   }
   const bool can_fuse = fused_eligible(h, io, frame_stride, rx_stride);
   const bool req_fused = h->path == RUB_PATH_FUSED;
-  if (req_fused && !can_fuse) {
+  if (req_fused && (!can_fuse || h->fused_unfit)) {
     set_error("fused path requested but the configuration / buffers are not eligible");
     return RUB_ERR_UNSUPPORTED;
   }
   const bool use_fused = req_fused || (h->path == RUB_PATH_AUTO && can_fuse);
   if (timed) cudaEventRecord(h->ev[0], h->stream);
-  rub_status st = use_fused ? run_fused(h, a, n_frames, timed) : run_staged(h, a, io, n_frames, timed);
+  rub_status st = (use_fused && !h->fused_unfit) ? run_fused(h, a, n_frames, timed) : run_staged(h, a, io, n_frames, timed);
+  // AUTO: a configuration whose fused kernel does not fit the SM (found at the first launch) is served staged
+  if (st == RUB_ERR_UNSUPPORTED && h->fused_unfit && !req_fused) st = run_staged(h, a, io, n_frames, timed);
   if (timed) cudaEventRecord(h->ev[1], h->stream);
   h->timed = timed && st == RUB_OK;
   return st;
@@ -641,18 +617,51 @@ extern "C" rub_status rub_comm_init(rub_rx *h, const uint8_t id[RUB_NCCL_UNIQUE_
   h->world = world;
   return RUB_OK;
 }
-// one ncclAllReduce(sum, uint64) over the 4*N error counters, on the handle's stream
+// Global error counters = sum over ranks of every rank's cumulative local counters.  Idempotent: the
+// handle's own counters are only read.  A snapshot of them is taken on the handle's stream (a 256-byte
+// device copy ordered after the batches issued so far), and ncclAllReduce(sum, uint64) turns it into
+// the global counters on a side stream, so the next batch never waits for the collective.  Snapshot and
+// result are double buffered; rub_rx_read_counters_global returns the latest reduction.
 extern "C" rub_status rub_allreduce_counters(rub_rx *h) {
   if (!h) return RUB_ERR_INVALID_ARG;
-  if (!h->comm) { if (h->world == 1) return RUB_OK; set_error("rub_comm_init not called"); return RUB_ERR_NCCL; }
+  if (!h->comm && h->world != 1) { set_error("rub_comm_init not called"); return RUB_ERR_NCCL; }
   CUDA_TRY(cudaSetDevice(h->device));
-  int r = g_nccl.AllReduce(h->d_counters, h->d_counters, 4 * h->h.N, /*ncclUint64*/ 5, /*ncclSum*/ 0, h->comm, h->stream);
-  if (r) { set_error("ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); return RUB_ERR_NCCL; }
-  h->launches += 1;
+  if (!h->s_comm) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->s_comm, cudaStreamNonBlocking));
+    CUDA_TRY(cudaMalloc(&h->d_snap, sizeof(uint64_t) * 4 * 32));
+    CUDA_TRY(cudaMemset(h->d_snap, 0, sizeof(uint64_t) * 4 * 32));
+    for (auto &e : h->cev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  const uint32_t i = h->n_reduce & 1;
+  uint64_t *snap = h->d_snap + 32 * i, *glob = h->d_snap + 64 + 32 * i;
+  // the reduction issued two calls ago read this snapshot slot
+  if (h->n_reduce >= 2) CUDA_TRY(cudaStreamWaitEvent(h->stream, h->cev[2 + i], 0));
+  CUDA_TRY(cudaMemcpyAsync(snap, h->d_counters, sizeof(uint64_t) * 4 * h->h.N, cudaMemcpyDeviceToDevice, h->stream));
+  CUDA_TRY(cudaEventRecord(h->cev[i], h->stream));
+  CUDA_TRY(cudaStreamWaitEvent(h->s_comm, h->cev[i], 0));
+  if (h->comm) {
+    int r = g_nccl.AllReduce(snap, glob, 4 * h->h.N, /*ncclUint64*/ 5, /*ncclSum*/ 0, h->comm, h->s_comm);
+    if (r) { set_error("ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); return RUB_ERR_NCCL; }
+    h->launches += 1;
+  } else {
+    CUDA_TRY(cudaMemcpyAsync(glob, snap, sizeof(uint64_t) * 4 * h->h.N, cudaMemcpyDeviceToDevice, h->s_comm));
+  }
+  CUDA_TRY(cudaEventRecord(h->cev[2 + i], h->s_comm));
+  h->n_reduce++;
+  return RUB_OK;
+}
+extern "C" rub_status rub_rx_read_counters_global(rub_rx *h, uint64_t *host_out) {
+  if (!h || !host_out) return RUB_ERR_INVALID_ARG;
+  if (!h->n_reduce) { set_error("read_counters_global: rub_allreduce_counters has not been called"); return RUB_ERR_INVALID_ARG; }
+  CUDA_TRY(cudaSetDevice(h->device));
+  const uint32_t i = (h->n_reduce - 1) & 1;
+  CUDA_TRY(cudaMemcpyAsync(host_out, h->d_snap + 64 + 32 * i, sizeof(uint64_t) * 4 * h->h.N, cudaMemcpyDeviceToHost, h->s_comm));
+  CUDA_TRY(cudaStreamSynchronize(h->s_comm));
   return RUB_OK;
 }
 extern "C" rub_status rub_comm_destroy(rub_rx *h) {
   if (!h) return RUB_ERR_INVALID_ARG;
+  if (h->s_comm) cudaStreamSynchronize(h->s_comm);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   h->comm = nullptr;
   return RUB_OK;
