@@ -1,11 +1,12 @@
 // rub_kernels_ws.cuh — the fused receive kernel, warp specialised (one persistent CTA per SM):
 //
-//   producer warp   one thread: TMA bulk loads of the next OFDM symbol (CP strip by address) into a
-//                   two-deep ring of landing buffers as soon as the detect warps release one
-//   FFT warps       NT threads (one warpgroup): in-place FFT of the N antennas of a symbol, software
-//                   pipelined over (stage, antenna) pairs; stage twiddles live in registers
+//   FFT warps       NT threads (one warpgroup): in-place FFT of the N antennas of a symbol in a two-deep
+//                   ring of landing buffers, stage by stage over the antennas (one barrier per
+//                   (stage, antenna)); the twiddles of a stage are read once per symbol into registers
 //   detect warps    LS accumulate / weights on training symbols; W*y -> gain -> slicer -> max-log
-//                   LLR -> packed bits -> error count on payload symbols, one symbol behind the FFT
+//                   LLR -> packed bits -> error count on payload symbols, one symbol behind the FFT.
+//                   The last detect warp to finish a symbol refills the buffer it frees: TMA bulk
+//                   loads of the symbol two ahead (CP strip by address), completed on an mbarrier
 //
 // replacing framesync::execute_mimo_decode (mimo/framing.cc:535-589), the LS/invert part of
 // estimate_channel (:801-832) and the demod/count loop of mimo/main.cc:1403-1410.
@@ -13,9 +14,10 @@
 // Why specialise: the monolithic kernel (rub_kernels_fused.cuh) runs FFT and detection one after the
 // other in the same 16 warps, so the store path idles during the FFT and the FMA path during
 // detection, and every thread carries the FFT's register footprint.  Here the two phases of
-// neighbouring symbols overlap, registers are re-partitioned with setmaxnreg (FFT threads keep
-// two antennas' points and all their twiddles in registers, detect threads need far fewer), and
-// the hand-offs are mbarriers (full -> y_ready -> empty) instead of CTA-wide barriers.
+// neighbouring symbols overlap, registers are re-partitioned with setmaxnreg, and the hand-offs are
+// mbarriers (full -> y_ready) and a shared-memory arrival counter instead of CTA-wide barriers.
+// Both loops are kept small on purpose (rolled over antennas / tasks): the SM has one 32 KB
+// instruction cache for both roles and a single FFT warp per scheduler hides no fetch latency.
 #pragma once
 #include <type_traits>
 
@@ -33,22 +35,22 @@ struct WsTraits {
   static constexpr int DET_WARPS = BLOCKS < 16 ? BLOCKS : 16;
   static constexpr int KPW = BLOCKS / DET_WARPS;                // blocks per detect warp and symbol
   static constexpr int DET_THREADS = DET_WARPS * 32;
-  static constexpr int THREADS = NT + DET_THREADS + 128;        // + the producer's warpgroup (one thread works)
+  static constexpr int THREADS = NT + DET_THREADS;
   static constexpr int BUF_ELEMS = N * PAD;
-  // register split (setmaxnreg acts on whole warpgroups, and ptxas sizes the launch allocation for
-  // the thread count rounded up to warpgroups): 768 threads launch with 80 registers each, the
-  // producer's warpgroup drops to 24 and hands 7168 registers to the FFT warpgroup
+  // register split (setmaxnreg acts on whole warpgroups; ptxas sizes the launch allocation for the
+  // thread count rounded up to warpgroups): 640 threads launch with 96 registers each, the detect
+  // warpgroups drop to 88 and hand 4096 registers to the FFT warpgroup (128 each)
   static constexpr int LAUNCH_REGS = 65536 / THREADS / 8 * 8;
-  static constexpr int AUX_REGS = 24;
-  static constexpr int FFT_REGS = (LAUNCH_REGS + (LAUNCH_REGS - AUX_REGS) * 128 / NT) / 8 * 8;
+  static constexpr int DET_REGS = LAUNCH_REGS - 8;
+  static constexpr int FFT_REGS = (LAUNCH_REGS + 8 * DET_THREADS / NT) / 8 * 8;
   static constexpr int TW_ELEMS = FftTw<LOG2M>::TOTAL;
   static_assert(PL::NSTG == 3, "three-stage plans only");
   static_assert(NT % 128 == 0 && DET_THREADS % 128 == 0, "roles are whole warpgroups (setmaxnreg)");
-  static_assert(N >= 2, "the pipelined FFT schedule needs two antenna regions");
+  static_assert(N >= 2 && N <= 4, "FFT barrier scheme needs two antenna regions; packed counters hold four streams");
   static_assert(KPW * DET_WARPS == BLOCKS, "block split");
   static size_t smem_bytes(int q) {
     return (size_t)2 * BUF_ELEMS * sizeof(cf) + (size_t)DET_WARPS * 2 * (256 * q) + (size_t)2 * N * M /* tx_data */ +
-           (size_t)TW_ELEMS * sizeof(cf) + 64 /* mbarriers */ + 64;
+           (size_t)TW_ELEMS * sizeof(cf) + 64 /* mbarriers, counters */ + 64;
   }
 };
 
@@ -59,6 +61,11 @@ template <int R>
 __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
 template <int R>
 __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+__device__ __forceinline__ unsigned atom_add_acq_rel_smem(unsigned *p, unsigned v) {
+  unsigned old;
+  asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+  return old;
+}
 
 // W*y and gain of one detection task: stream s of a 64-carrier block (lane = 2 adjacent carriers)
 template <int N>
@@ -72,11 +79,11 @@ __device__ __forceinline__ void ws_dot(const TaskRegs<N> &t, const float4 *y4, c
   z0 = cscale(wy_dot<N>(w0, y0), t.g.x);
   z1 = cscale(wy_dot<N>(w1, y1), t.g.y);
 }
-// the rest of the task: slicer, max-log LLRs (staged in [k][bit] order at lp), packed bits, error count
+// the rest of the task: slicer, max-log LLRs (staged in [k][bit] order at lp), packed bits; returns the two
+// demodulated symbols (sym0 | sym1 << 8)
 template <int MB>
-__device__ __forceinline__ void ws_demap(const ChainArgs &a, const DemapConst &dc, const float *refs, cf z0, cf z1, float2 is,
-                                         long long o, float *lp, unsigned txv, unsigned &ec,
-                                         unsigned long long pol_stream) {
+__device__ __forceinline__ unsigned ws_demap(const ChainArgs &a, const DemapConst &dc, const float *refs, cf z0, cf z1, float2 is,
+                                             long long o, float *lp, unsigned long long pol_stream) {
   constexpr int Q = 2 * MB;
   const int lane = threadIdx.x & 31;
   if (a.eq) st_hint4(a.eq + o, make_float4(z0.x, z0.y, z1.x, z1.y), pol_stream);
@@ -114,76 +121,67 @@ __device__ __forceinline__ void ws_demap(const ChainArgs &a, const DemapConst &d
       }
     }
   }
-  if (a.tx_data) {
-    const unsigned x = rx2 ^ txv;
-    ec += (unsigned)__popc(x) + (((x & 0xffu) != 0u ? 1u : 0u) << 16) + (((x >> 8) != 0u ? 1u : 0u) << 16);
-  }
+  return rx2;
 }
 
-template <int LOG2M, int N>
+template <int LOG2M, int N, int MB>
 __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedArgs fa, DemapConst dc) {
   using TR = WsTraits<LOG2M, N>;
   using FF = Fft<LOG2M>;
   using TW = FftTw<LOG2M>;
   constexpr int M = TR::M, NT = TR::NT, PAD = TR::PAD, DET_WARPS = TR::DET_WARPS, DET_THREADS = TR::DET_THREADS, KPW = TR::KPW;
+  constexpr int Q = 2 * MB;
   const ChainArgs &a = fa.a;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   cf *buf0 = reinterpret_cast<cf *>(smem_raw);
   cf *buf1 = buf0 + TR::BUF_ELEMS;
   unsigned char *stage_base = reinterpret_cast<unsigned char *>(buf1 + TR::BUF_ELEMS);
-  const int q = a.q;
-  const int stage_stride = 256 * q;  // 64 carriers x q LLRs
+  constexpr int stage_stride = 256 * Q;  // 64 carriers x Q LLRs
   unsigned char *txbuf = stage_base + (size_t)DET_WARPS * 2 * stage_stride;              // [2][N][M] tx symbols
   cf *tw_s = reinterpret_cast<cf *>(txbuf + 2 * N * M);                                   // stage twiddles, copied once
-  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(tw_s + TR::TW_ELEMS);  // full[2], yrdy[2], empty[2]
+  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(tw_s + TR::TW_ELEMS);  // full[2], yrdy[2]
+  unsigned *done = reinterpret_cast<unsigned *>(mbar + 4);                                // detect warps done with buffer [2]
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int nsym = a.T + a.D;
+  const int nf_cta = (a.n_frames - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int total = nf_cta * nsym;  // flat (frame, symbol) sequence of this CTA
+  const unsigned long long pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
+
+  // TMA loads of symbol `sym` of this CTA's frame number `fl` into ring slot b (one thread)
+  auto issue_load = [&](int b, int fl, int sym) {
+    const long long frame = (long long)blockIdx.x + (long long)fl * gridDim.x;
+    cf *dst = b ? buf1 : buf0;
+    constexpr unsigned sym_bytes = (unsigned)(M * sizeof(cf));
+    const bool with_tx = a.tx_data && sym >= a.T;
+    mbar_expect_tx(&mbar[b], sym_bytes * N + (with_tx ? N * M : 0));
+    const cf *src = a.iq + frame * a.frame_stride + a.first_sample + (long long)sym * a.L + a.cp;
+#pragma unroll
+    for (int r = 0; r < N; r++)
+      bulk_load(dst + (size_t)r * PAD, src + (long long)r * a.rx_stride, sym_bytes, &mbar[b], pol_stream);
+    if (with_tx) {
+      // the transmitted symbol indices of this OFDM symbol ride on the same mbarrier
+      const unsigned char *tsrc = a.tx_data + (frame * N * a.D + (sym - a.T)) * (long long)M;
+#pragma unroll
+      for (int s = 0; s < N; s++) bulk_load(txbuf + (b * N + s) * M, tsrc + (long long)s * a.D * M, M, &mbar[b], pol_stream);
+    }
+  };
+
   if (tid == 0) {
     mbar_init(&mbar[0], 1);
     mbar_init(&mbar[1], 1);
     mbar_init(&mbar[2], TR::FFT_WARPS);
     mbar_init(&mbar[3], TR::FFT_WARPS);
-    mbar_init(&mbar[4], DET_WARPS);
-    mbar_init(&mbar[5], DET_WARPS);
+    done[0] = 0;
+    done[1] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
+    if (total > 0) issue_load(0, 0, 0);
+    if (total > 1) issue_load(1, nsym > 1 ? 0 : 1, nsym > 1 ? 1 : 0);
   }
   for (int i = tid; i < TR::TW_ELEMS; i += TR::THREADS) tw_s[i] = a.tw[i];
   __syncthreads();
-
-  const int nf_cta = (a.n_frames - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int total = nf_cta * nsym;  // flat (frame, symbol) sequence of this CTA
-  const unsigned long long pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
-
-  if (warp >= TR::FFT_WARPS + DET_WARPS) {
-    // ================================ producer ================================
-    reg_dec<TR::AUX_REGS>();
-    if (tid != NT + DET_THREADS) return;
-    const unsigned sym_bytes = (unsigned)(M * sizeof(cf));
-    int fl = 0, sym = 0;
-    for (int g = 0; g < total; g++) {
-      const int b = g & 1;
-      if (g >= 2) mbar_wait(&mbar[4 + b], (unsigned)(((g - 2) >> 1) & 1));  // the detect warps are done with symbol g-2
-      const long long frame = (long long)blockIdx.x + (long long)fl * gridDim.x;
-      cf *dst = b ? buf1 : buf0;
-      const bool with_tx = a.tx_data && sym >= a.T;
-      mbar_expect_tx(&mbar[b], sym_bytes * N + (with_tx ? N * M : 0));
-      const cf *src = a.iq + frame * a.frame_stride + a.first_sample + (long long)sym * a.L + a.cp;
-#pragma unroll
-      for (int r = 0; r < N; r++)
-        bulk_load(dst + (size_t)r * PAD, src + (long long)r * a.rx_stride, sym_bytes, &mbar[b], pol_stream);
-      if (with_tx) {
-        // the transmitted symbol indices of this OFDM symbol ride on the same mbarrier
-        const unsigned char *tsrc = a.tx_data + (frame * N * a.D + (sym - a.T)) * (long long)M;
-#pragma unroll
-        for (int s = 0; s < N; s++) bulk_load(txbuf + (b * N + s) * M, tsrc + (long long)s * a.D * M, M, &mbar[b], pol_stream);
-      }
-      if (++sym == nsym) { sym = 0; fl++; }
-    }
-    return;
-  }
 
   if (warp < TR::FFT_WARPS) {
     // ================================ FFT warps ================================
@@ -195,31 +193,35 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
       cf *buf = b ? buf1 : buf0;
       const float scale = (sym >= a.T) ? a.dn : 1.0f;
       mbar_wait(&mbar[b], (unsigned)((g >> 1) & 1));
-      // pair p = (stage p / N, antenna p % N); loads of pair p+1 are issued before pair p is computed.
-      // In place: a barrier separates every thread's loads of a pair from any thread's stores of it,
-      // and the stores of a pair from the next stage's loads of the same antenna (N >= 2 pairs later).
-      // the twiddles of a stage depend on the thread only: read once per symbol, used for all N antennas
-      cf va[FF::PTS], vb[FF::PTS], tw[FF::S1::NTW > FF::S2::NTW ? FF::S1::NTW : FF::S2::NTW];
-      auto load_pair = [&](int p, cf *v) {
-        cf *reg = buf + (size_t)(p % N) * PAD;
-        if (p / N == 0) FF::S0::template load<false>(ft, reg, v);
-        else if (p / N == 1) FF::S1::template load<true>(ft, reg, v);
-        else FF::S2::template load<true>(ft, reg, v);
-      };
-      auto finish_pair = [&](int p, cf *v) {
-        cf *reg = buf + (size_t)(p % N) * PAD;
-        if (p / N == 0) { FF::S0::compute(ft, v, nullptr); FF::S0::template store<true, false>(ft, v, reg, 1.f); }
-        else if (p / N == 1) { FF::S1::compute_pre(v, tw); FF::S1::template store<true, false>(ft, v, reg, 1.f); }
-        else { FF::S2::compute_pre(v, tw); FF::S2::template store<false, true>(ft, v, reg, scale); }
-      };
-      load_pair(0, va);
-#pragma unroll
-      for (int p = 0; p < 3 * N; p++) {
+      // In place, stage by stage over the antennas.  The barrier between a pair's loads and its
+      // stores also orders the stores of the previous pair before the next stage's loads of that
+      // antenna (N >= 2 pairs later), so one barrier per (stage, antenna) suffices.
+      cf v[FF::PTS], tw[FF::S1::NTW > FF::S2::NTW ? FF::S1::NTW : FF::S2::NTW];
+#pragma unroll 1
+      for (int r = 0; r < N; r++) {
+        cf *reg = buf + (size_t)r * PAD;
+        FF::S0::template load<false>(ft, reg, v);
         named_bar(1, NT);
-        if (p == N) FF::S1::load_twiddles(ft, tw_s + TW::OFF1, tw);
-        if (p == 2 * N) FF::S2::load_twiddles(ft, tw_s + TW::OFF2, tw);
-        if (p + 1 < 3 * N) load_pair(p + 1, (p & 1) ? va : vb);
-        finish_pair(p, (p & 1) ? vb : va);
+        FF::S0::compute(ft, v, nullptr);
+        FF::S0::template store<true, false>(ft, v, reg, 1.f);
+      }
+      FF::S1::load_twiddles(ft, tw_s + TW::OFF1, tw);
+#pragma unroll 1
+      for (int r = 0; r < N; r++) {
+        cf *reg = buf + (size_t)r * PAD;
+        FF::S1::template load<true>(ft, reg, v);
+        named_bar(1, NT);
+        FF::S1::compute_pre(v, tw);
+        FF::S1::template store<true, false>(ft, v, reg, 1.f);
+      }
+      FF::S2::load_twiddles(ft, tw_s + TW::OFF2, tw);
+#pragma unroll 1
+      for (int r = 0; r < N; r++) {
+        cf *reg = buf + (size_t)r * PAD;
+        FF::S2::template load<true>(ft, reg, v);
+        named_bar(1, NT);
+        FF::S2::compute_pre(v, tw);
+        FF::S2::template store<false, true>(ft, v, reg, scale);
       }
       // Y complete: every lane's stores are ordered before lane 0's release-arrive
       __syncwarp();
@@ -230,32 +232,31 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
   }
 
   // ================================ detect warps ================================
+  reg_dec<TR::DET_REGS>();
   const int dtid = tid - NT, dwarp = warp - TR::FFT_WARPS;
   cf *Wc = fa.scratchW + (size_t)blockIdx.x * N * N * M;
   float *gc = fa.scratchG + (size_t)blockIdx.x * 2 * N * M, *ic = gc + (size_t)N * M;
   float refs[4];  // liquid ref[k] = 2^k * alpha, most significant first
 #pragma unroll
-  for (int i = 0; i < 4; i++) refs[i] = (i < q / 2) ? (float)(1u << (q / 2 - 1 - i)) * dc.alpha : 0.f;
+  for (int i = 0; i < 4; i++) refs[i] = (i < MB) ? (float)(1u << (MB - 1 - i)) * dc.alpha : 0.f;
   const int koff = dwarp * 64 + 2 * lane;                // first carrier of this lane in block kb = 0
   constexpr int KSTEP = 64 * DET_WARPS;                  // carrier distance between a warp's blocks
   unsigned char *slot0 = stage_base + (size_t)(dwarp * 2) * stage_stride;
-  unsigned ec[N];  // per-lane error counts of the current frame: bit errors | symbol errors << 16
-#pragma unroll
-  for (int s = 0; s < N; s++) ec[s] = 0;
-  // the packed 16-bit fields must survive the warp sum: flush before 32 lanes x bit errors can reach 65536
-  const int flush_every = max(1, 2047 / (KPW * 2 * q));
+  // per-lane error counts, 16 bits per stream: bit errors in eb, symbol errors in es
+  unsigned long long eb = 0, es = 0;
+  // the 16-bit fields must survive the warp sum: flush before 32 lanes x bit errors can reach 65536
+  const int flush_every = max(1, 2047 / (KPW * 2 * Q));
   int since_flush = 0;
   auto flush_counts = [&](int nsyms_flushed) {
-#pragma unroll
-    for (int s = 0; s < N; s++) {
-      const unsigned v = __reduce_add_sync(0xffffffffu, ec[s]);
-      ec[s] = 0;
-      if (lane == 0 && a.counters) {
-        atomicAdd(&a.counters[s * 4 + 0], (unsigned long long)(v & 0xffffu));
-        atomicAdd(&a.counters[s * 4 + 1], (unsigned long long)nsyms_flushed * KPW * 64 * q);
-        atomicAdd(&a.counters[s * 4 + 2], (unsigned long long)(v >> 16));
-        atomicAdd(&a.counters[s * 4 + 3], (unsigned long long)nsyms_flushed * KPW * 64);
-      }
+    const unsigned b0 = __reduce_add_sync(0xffffffffu, (unsigned)eb), b1 = __reduce_add_sync(0xffffffffu, (unsigned)(eb >> 32));
+    const unsigned s0 = __reduce_add_sync(0xffffffffu, (unsigned)es), s1 = __reduce_add_sync(0xffffffffu, (unsigned)(es >> 32));
+    eb = 0; es = 0;
+    if (lane < N && a.counters) {
+      const unsigned bw = (lane & 2) ? b1 : b0, sw = (lane & 2) ? s1 : s0;
+      atomicAdd(&a.counters[lane * 4 + 0], (unsigned long long)((bw >> (16 * (lane & 1))) & 0xffffu));
+      atomicAdd(&a.counters[lane * 4 + 1], (unsigned long long)nsyms_flushed * KPW * 64 * Q);
+      atomicAdd(&a.counters[lane * 4 + 2], (unsigned long long)((sw >> (16 * (lane & 1))) & 0xffffu));
+      atomicAdd(&a.counters[lane * 4 + 3], (unsigned long long)nsyms_flushed * KPW * 64);
     }
   };
 
@@ -265,15 +266,33 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
     const long long frame = (long long)blockIdx.x + (long long)fl * gridDim.x;
     const cf *buf = b ? buf1 : buf0;
     const bool payload = sym >= a.T;
+    const cf *wp = Wc + koff;         // W[s][0][k] of the current task (this lane's carriers)
+    const float *gp = gc + koff;      // gain[s][k]; isig follows N*M floats later
     TaskRegs<N> w;
-    if (payload) task_load<N, M>(w, WarpCtx{Wc + koff, gc + koff, nullptr, 0, koff, 0}, 0, 0, pol_keep);  // before Y is needed
+    auto load_w = [&]() {
+#pragma unroll
+      for (int r = 0; r < N; r++) w.w[r] = ld_hint4(wp + r * M, pol_keep);
+      w.g = ld_hint2(gp, pol_keep);
+      w.is = ld_hint2(gp + N * M, pol_keep);
+    };
+    if (payload) load_w();  // W of the first task: requested before Y is needed
     if (sym == 0 && fl > 0) named_bar(2, DET_THREADS);  // every warp is done reading the previous frame's W
     mbar_wait(&mbar[2 + b], (unsigned)((g >> 1) & 1));
+    // This warp's last generic-proxy access to the ring slot is done.  The last warp to say so refills the
+    // slot with the symbol two ahead.
     auto release_buf = [&]() {
-      // this warp's last generic-proxy access to `buf` is done: the producer may refill it by TMA
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&mbar[4 + b]);
+      if (lane == 0) {
+        if (atom_add_acq_rel_smem(&done[b], 1u) == (unsigned)(DET_WARPS - 1)) {
+          done[b] = 0;
+          if (g + 2 < total) {
+            int s2 = sym + 2, f2 = fl;
+            if (s2 >= nsym) { s2 -= nsym; f2++; }
+            issue_load(b, f2, s2);
+          }
+        }
+      }
     };
     if (!payload) {
       // ---------------- LS accumulate (mimo/framing.cc:801-815) ----------------
@@ -301,6 +320,7 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
       if (sym == a.T - 1) {
         // ---------------- weights (mimo/framing.cc:817-832) ----------------
         named_bar(2, DET_THREADS);
+#pragma unroll 1
         for (int k = dtid; k < M; k += DET_THREADS) {
           cf G[N * N], W[N * N];
           float gain[N], isig[N];
@@ -323,54 +343,53 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
       }
     } else {
       // ---------------- detect + demap + count ----------------
-      const long long symbase = (frame * N * a.D + (sym - a.T)) * (long long)M + koff;  // stream 0, block 0, this lane
-      const int DM = a.D * M;
+      long long o = (frame * N * a.D + (sym - a.T)) * (long long)M + koff;  // stream 0, block 0, this lane
+      const long long DM = (long long)a.D * M;
       const unsigned char *txl = txbuf + b * N * M + koff;
-      const WarpCtx wc{Wc + koff, gc + koff, nullptr, 0, koff, 0};
-      auto detect = [&](auto mbtag) {
-        constexpr int MB = decltype(mbtag)::value, Q = 2 * MB;
+      int it = 0;
+#pragma unroll 1
+      for (int kb = 0; kb < KPW; kb++) {
+        float4 y4[N];
 #pragma unroll
-        for (int kb = 0; kb < KPW; kb++) {
-          float4 y4[N];
-#pragma unroll
-          for (int r = 0; r < N; r++) y4[r] = *reinterpret_cast<const float4 *>(buf + (size_t)r * PAD + koff + kb * KSTEP);
-          unsigned txv[N];
+        for (int r = 0; r < N; r++) y4[r] = *reinterpret_cast<const float4 *>(buf + (size_t)r * PAD + koff + kb * KSTEP);
+        unsigned long long txp = 0;  // reference symbols of the N streams, 16 bits each
+        if (a.tx_data) {
 #pragma unroll
           for (int s = 0; s < N; s++)
-            txv[s] = a.tx_data ? (unsigned)*reinterpret_cast<const unsigned short *>(txl + s * M + kb * KSTEP) : 0u;
-          if (kb == KPW - 1) release_buf();  // Y and the reference symbols are in registers
-#pragma unroll
-          for (int s = 0; s < N; s++) {
-            const int it = kb * N + s;
-            cf z0, z1;
-            const float2 is = w.is;
-            ws_dot<N>(w, y4, z0, z1);
-            // W of the next task lands in the registers the products just released
-            if (it + 1 < KPW * N) task_load<N, M>(w, wc, (s + 1) % N, ((s + 1 == N) ? kb + 1 : kb) * KSTEP, pol_keep);
-            unsigned char *slot = slot0 + (it & 1) * stage_stride;
-            if (a.llr) {
-              // the bulk store issued two tasks ago from this staging slot must have drained
-              if (lane == 0) bulk_wait_read<1>();
-              __syncwarp();
-            }
-            const long long o = symbase + (long long)s * DM + kb * KSTEP;
-            ws_demap<MB>(a, dc, refs, z0, z1, is, o, reinterpret_cast<float *>(slot) + lane * 2 * Q, txv[s], ec[s], pol_stream);
-            if (a.llr) {
-              fence_async_smem();
-              __syncwarp();
-              if (lane == 0) {
-                bulk_store(a.llr + (o - 2 * lane) * Q, slot, (unsigned)(64 * Q * 4), pol_stream);
-                bulk_commit();
-              }
+            txp |= (unsigned long long)*reinterpret_cast<const unsigned short *>(txl + s * M + kb * KSTEP) << (16 * s);
+        }
+        if (kb == KPW - 1) release_buf();  // Y and the reference symbols are in registers
+#pragma unroll 1
+        for (int s = 0; s < N; s++, it++) {
+          cf z0, z1;
+          const float2 is = w.is;
+          ws_dot<N>(w, y4, z0, z1);
+          // W of the next task lands in the registers the products just released
+          if (s + 1 < N) { wp += N * M; gp += M; }
+          else { wp += KSTEP - (N - 1) * N * M; gp += KSTEP - (N - 1) * M; }
+          if (it + 1 < KPW * N) load_w();
+          unsigned char *slot = slot0 + (it & 1) * stage_stride;
+          if (a.llr) {
+            // the bulk store issued two tasks ago from this staging slot must have drained
+            if (lane == 0) bulk_wait_read<1>();
+            __syncwarp();
+          }
+          const unsigned rx2 = ws_demap<MB>(a, dc, refs, z0, z1, is, o, reinterpret_cast<float *>(slot) + lane * 2 * Q, pol_stream);
+          if (a.llr) {
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              bulk_store(a.llr + (o - 2 * lane) * Q, slot, (unsigned)(64 * Q * 4), pol_stream);
+              bulk_commit();
             }
           }
+          if (a.tx_data) {
+            const unsigned x = rx2 ^ ((unsigned)(txp >> (16 * s)) & 0xffffu);
+            eb += (unsigned long long)__popc(x) << (16 * s);
+            es += (unsigned long long)(((x & 0xffu) != 0u ? 1u : 0u) + ((x >> 8) != 0u ? 1u : 0u)) << (16 * s);
+          }
+          o += (s + 1 < N) ? DM : (long long)KSTEP - (N - 1) * DM;
         }
-      };
-      switch (q) {
-        case 2: detect(std::integral_constant<int, 1>{}); break;
-        case 4: detect(std::integral_constant<int, 2>{}); break;
-        case 6: detect(std::integral_constant<int, 3>{}); break;
-        default: detect(std::integral_constant<int, 4>{}); break;
       }
       if (a.tx_data && (++since_flush == flush_every || sym == nsym - 1)) { flush_counts(since_flush); since_flush = 0; }
     }

@@ -12,14 +12,33 @@ bool ws_has_instance(uint32_t l2, uint32_t N) {
 #undef X
   return false;
 }
-template <int LOG2M, int N>
-static cudaError_t prepare(uint32_t q, size_t *smem_out, int *occ) {
+template <int LOG2M, int N, int MB>
+static cudaError_t prepare_mb(size_t *smem_out, int *occ) {
   using TR = WsTraits<LOG2M, N>;
-  const size_t smem = TR::smem_bytes((int)q);
-  cudaError_t e = cudaFuncSetAttribute(k_rx_ws<LOG2M, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = TR::smem_bytes(2 * MB);
+  cudaError_t e = cudaFuncSetAttribute(k_rx_ws<LOG2M, N, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   *smem_out = smem;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_rx_ws<LOG2M, N>, TR::THREADS, smem);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_rx_ws<LOG2M, N, MB>, TR::THREADS, smem);
+}
+template <int LOG2M, int N>
+static cudaError_t prepare(uint32_t q, size_t *smem_out, int *occ) {
+  switch (q) {
+    case 2: return prepare_mb<LOG2M, N, 1>(smem_out, occ);
+    case 4: return prepare_mb<LOG2M, N, 2>(smem_out, occ);
+    case 6: return prepare_mb<LOG2M, N, 3>(smem_out, occ);
+    default: return prepare_mb<LOG2M, N, 4>(smem_out, occ);
+  }
+}
+template <int LOG2M, int N>
+static void launch(int grid, size_t smem, cudaStream_t st, const FusedArgs &fa, const DemapConst &dc) {
+  constexpr int T = WsTraits<LOG2M, N>::THREADS;
+  switch (fa.a.q) {
+    case 2: k_rx_ws<LOG2M, N, 1><<<grid, T, smem, st>>>(fa, dc); break;
+    case 4: k_rx_ws<LOG2M, N, 2><<<grid, T, smem, st>>>(fa, dc); break;
+    case 6: k_rx_ws<LOG2M, N, 3><<<grid, T, smem, st>>>(fa, dc); break;
+    default: k_rx_ws<LOG2M, N, 4><<<grid, T, smem, st>>>(fa, dc); break;
+  }
 }
 cudaError_t ws_prepare(uint32_t l2, uint32_t N, uint32_t q, size_t *smem, int *occ) {
 #define X(L, NN) if (l2 == L && N == NN) return prepare<L, NN>(q, smem, occ);
@@ -28,7 +47,7 @@ cudaError_t ws_prepare(uint32_t l2, uint32_t N, uint32_t q, size_t *smem, int *o
   return cudaErrorInvalidValue;
 }
 void ws_launch(uint32_t l2, uint32_t N, int grid, size_t smem, cudaStream_t st, const FusedArgs &fa, const DemapConst &dc) {
-#define X(L, NN) if (l2 == L && N == NN) { k_rx_ws<L, NN><<<grid, WsTraits<L, NN>::THREADS, smem, st>>>(fa, dc); return; }
+#define X(L, NN) if (l2 == L && N == NN) { launch<L, NN>(grid, smem, st, fa, dc); return; }
   RUB_WS_LIST(X)
 #undef X
 }
