@@ -40,6 +40,9 @@ struct FusedArgs {
   float *scratchG;   // [grid][2][N][M]  gain, isig
   int llr_stage_bytes;  // 256*q
   WeightMode wm;
+  // warp-specialised kernel only (rub_kernels_ws.cuh)
+  cf *scratchAcc;            // [grid][N*N][M] LS estimate of the next frame, written by the FFT warps
+  const unsigned char *sgn8; // [tx][code][M/R2] sign bits of the access codes in last-stage register order
 };
 
 }  // namespace rub

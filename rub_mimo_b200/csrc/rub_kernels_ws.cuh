@@ -1,23 +1,29 @@
 // rub_kernels_ws.cuh — the fused receive kernel, warp specialised (one persistent CTA per SM):
 //
-//   FFT warps       NT threads (one warpgroup): in-place FFT of the N antennas of a symbol in a two-deep
-//                   ring of landing buffers, stage by stage over the antennas (one barrier per
-//                   (stage, antenna)); the twiddles of a stage are read once per symbol into registers
-//   detect warps    LS accumulate / weights on training symbols; W*y -> gain -> slicer -> max-log
-//                   LLR -> packed bits -> error count on payload symbols, one symbol behind the FFT.
-//                   The last detect warp to finish a symbol refills the buffer it frees: TMA bulk
-//                   loads of the symbol two ahead (CP strip by address), completed on an mbarrier
+//   FFT warps       NT threads (one warpgroup).  Payload symbols: in-place FFT of the N antennas in a
+//                   two-deep ring of landing buffers, stage by stage over the antennas, handed to the
+//                   detect warps through an mbarrier.  Training symbols never reach the detect warps:
+//                   they are transformed one antenna at a time in a small landing pair of their own
+//                   and the LS estimate is accumulated straight from the last stage's registers into
+//                   the frame's G scratch.  The training symbols of frame f+1 are interleaved with
+//                   the payload symbols of frame f, so the FFT load is even over time.
+//   detect warps    weights once per frame, then W*y -> gain -> slicer -> max-log LLR -> packed bits
+//                   -> error count per payload symbol, one symbol behind the FFT.  The last detect
+//                   warp to finish a symbol refills the ring slot it frees (TMA bulk loads of the
+//                   payload symbol two ahead, CP strip by address, completed on an mbarrier).
 //
 // replacing framesync::execute_mimo_decode (mimo/framing.cc:535-589), the LS/invert part of
 // estimate_channel (:801-832) and the demod/count loop of mimo/main.cc:1403-1410.
 //
 // Why specialise: the monolithic kernel (rub_kernels_fused.cuh) runs FFT and detection one after the
 // other in the same 16 warps, so the store path idles during the FFT and the FMA path during
-// detection, and every thread carries the FFT's register footprint.  Here the two phases of
-// neighbouring symbols overlap, registers are re-partitioned with setmaxnreg, and the hand-offs are
-// mbarriers (full -> y_ready) and a shared-memory arrival counter instead of CTA-wide barriers.
-// Both loops are kept small on purpose (rolled over antennas / tasks): the SM has one 32 KB
-// instruction cache for both roles and a single FFT warp per scheduler hides no fetch latency.
+// detection, and every thread carries the FFT's register footprint.  Here the two phases overlap,
+// registers are re-partitioned with setmaxnreg, and the hand-offs are mbarriers and a shared-memory
+// arrival counter instead of CTA-wide barriers.  Both loops are kept small on purpose (rolled over
+// antennas / tasks): the SM has one 32 KB instruction cache for both roles and a single FFT warp
+// per scheduler hides no fetch latency.  Frame f+1 is estimated while frame f is detected: its LS
+// estimate goes to a scratch of its own (ordinary L2 policy), the W/gain/isig scratch that the detect
+// warps re-read D times per frame stays a single evict_last set per CTA.
 #pragma once
 #include <type_traits>
 
@@ -43,16 +49,35 @@ struct WsTraits {
   static constexpr int LAUNCH_REGS = 65536 / THREADS / 8 * 8;
   static constexpr int DET_REGS = LAUNCH_REGS - 8;
   static constexpr int FFT_REGS = (LAUNCH_REGS + 8 * DET_THREADS / NT) / 8 * 8;
-  static constexpr int TW_ELEMS = FftTw<LOG2M>::TOTAL;
   static_assert(PL::NSTG == 3, "three-stage plans only");
   static_assert(NT % 128 == 0 && DET_THREADS % 128 == 0, "roles are whole warpgroups (setmaxnreg)");
   static_assert(N >= 2 && N <= 4, "FFT barrier scheme needs two antenna regions; packed counters hold four streams");
   static_assert(KPW * DET_WARPS == BLOCKS, "block split");
   static size_t smem_bytes(int q) {
-    return (size_t)2 * BUF_ELEMS * sizeof(cf) + (size_t)DET_WARPS * 2 * (256 * q) + (size_t)2 * N * M /* tx_data */ +
-           (size_t)TW_ELEMS * sizeof(cf) + 64 /* mbarriers, counters */ + 64;
+    return (size_t)2 * BUF_ELEMS * sizeof(cf) /* payload ring */ + (size_t)2 * PAD * sizeof(cf) /* training landing pair */ +
+           (size_t)DET_WARPS * 2 * (256 * q) /* LLR staging */ + (size_t)FftTw<LOG2M>::CNT1 * sizeof(cf) /* stage-1 twiddles */ +
+           128 /* mbarriers, counters */;
   }
 };
+
+// Host side: sign bytes of the access codes in the register order of the last FFT stage.  Thread ft, butterfly
+// b of that stage ends up with the carriers k = (j / NS2) * NS2 * R2 + j % NS2 + t2 * NS2, j = ft + b * NT,
+// t2 = 0..R2-1: byte [tx][code][j] carries their signs, bit t2 set = S1 is -1.
+template <int LOG2M>
+void ws_pack_signs(int N, int nac, const float *sgn /* [tx][code][M] */, unsigned char *out /* [tx][code][M/R2] */) {
+  using FF = Fft<LOG2M>;
+  constexpr int M = FF::M, NS2 = FftTw<LOG2M>::NS2, R2 = FF::S2::P / FF::S2::B;
+  static_assert(R2 <= 8, "one byte per butterfly");
+  for (int tc = 0; tc < N * nac; tc++)
+    for (int j = 0; j < M / R2; j++) {
+      unsigned v = 0;
+      for (int t2 = 0; t2 < R2; t2++) {
+        const int k = (j / NS2) * NS2 * R2 + (j % NS2) + t2 * NS2;
+        if (sgn[(size_t)tc * M + k] < 0.f) v |= 1u << t2;
+      }
+      out[(size_t)tc * (M / R2) + j] = (unsigned char)v;
+    }
+}
 
 __device__ __forceinline__ void named_bar(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -83,9 +108,9 @@ __device__ __forceinline__ void ws_dot(const TaskRegs<N> &t, const float4 *y4, c
 // demodulated symbols (sym0 | sym1 << 8)
 template <int MB>
 __device__ __forceinline__ unsigned ws_demap(const ChainArgs &a, const DemapConst &dc, const float *refs, cf z0, cf z1, float2 is,
-                                             long long o, float *lp, unsigned long long pol_stream) {
+                                             long long o, float *lp, unsigned short *bp, unsigned long long pol_stream,
+                                             int lane) {
   constexpr int Q = 2 * MB;
-  const int lane = threadIdx.x & 31;
   if (a.eq) st_hint4(a.eq + o, make_float4(z0.x, z0.y, z1.x, z1.y), pol_stream);
   const unsigned si0 = slice_axis_refs<MB>(z0.x, refs), sq0 = slice_axis_refs<MB>(z0.y, refs);
   const unsigned si1 = slice_axis_refs<MB>(z1.x, refs), sq1 = slice_axis_refs<MB>(z1.y, refs);
@@ -113,7 +138,6 @@ __device__ __forceinline__ unsigned ws_demap(const ChainArgs &a, const DemapCons
     const unsigned p2 = __shfl_xor_sync(0xffffffffu, v4, 2);
     if ((lane & 3) == 0) {
       const unsigned long long v8 = ((unsigned long long)v4 << (4 * Q)) | p2;  // 8Q bits = Q bytes
-      unsigned short *bp = reinterpret_cast<unsigned short *>(a.bits + ((o - 2 * lane) >> 3) * Q + (lane >> 2) * Q);
 #pragma unroll
       for (int i = 0; i < Q / 2; i++) {
         const unsigned hw = (unsigned)(v8 >> (16 * (Q / 2 - 1 - i))) & 0xffffu;
@@ -133,39 +157,49 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
   constexpr int Q = 2 * MB;
   const ChainArgs &a = fa.a;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  cf *buf0 = reinterpret_cast<cf *>(smem_raw);
-  cf *buf1 = buf0 + TR::BUF_ELEMS;
-  unsigned char *stage_base = reinterpret_cast<unsigned char *>(buf1 + TR::BUF_ELEMS);
+  cf *ring = reinterpret_cast<cf *>(smem_raw);                       // [2][N][PAD] payload symbols
+  cf *land = ring + 2 * TR::BUF_ELEMS;                               // [2][PAD]    training symbols, one antenna each
+  unsigned char *stage_base = reinterpret_cast<unsigned char *>(land + 2 * PAD);
   constexpr int stage_stride = 256 * Q;  // 64 carriers x Q LLRs
-  unsigned char *txbuf = stage_base + (size_t)DET_WARPS * 2 * stage_stride;              // [2][N][M] tx symbols
-  cf *tw_s = reinterpret_cast<cf *>(txbuf + 2 * N * M);                                   // stage twiddles, copied once
-  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(tw_s + TR::TW_ELEMS);  // full[2], yrdy[2]
-  unsigned *done = reinterpret_cast<unsigned *>(mbar + 4);                                // detect warps done with buffer [2]
+  // mbarriers: full[2] (ring slot loaded), yrdy[2] (ring slot transformed), tfull[2] (landing slot loaded),
+  // gdone at 6 (a frame's G is complete), wdone at 7 (the weights of a frame are computed)
+  cf *tw_s = reinterpret_cast<cf *>(stage_base + (size_t)DET_WARPS * 2 * stage_stride);  // stage-1 twiddles, copied once
+  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(tw_s + TW::CNT1);
+  unsigned *done = reinterpret_cast<unsigned *>(mbar + 8);           // detect warps done with ring slot [2]
 
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x;
+  int lane;  // kept in a register: ptxas would otherwise re-read SR_TID.X (a long-latency S2R) at every use
+  asm volatile("mov.u32 %0, %1;" : "=r"(lane) : "r"(tid & 31));
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  const int nsym = a.T + a.D;
-  const int nf_cta = (a.n_frames - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int total = nf_cta * nsym;  // flat (frame, symbol) sequence of this CTA
+  const int D = a.D;                 // payload symbols per frame
+  const int TU = N * N * a.nac;      // training units ((symbol, antenna) transforms) per frame
+  const int nf = (a.n_frames - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // frames of this CTA
   const unsigned long long pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
+  constexpr unsigned sym_bytes = (unsigned)(M * sizeof(cf));
 
-  // TMA loads of symbol `sym` of this CTA's frame number `fl` into ring slot b (one thread)
-  auto issue_load = [&](int b, int fl, int sym) {
-    const long long frame = (long long)blockIdx.x + (long long)fl * gridDim.x;
-    cf *dst = b ? buf1 : buf0;
-    constexpr unsigned sym_bytes = (unsigned)(M * sizeof(cf));
-    const bool with_tx = a.tx_data && sym >= a.T;
-    mbar_expect_tx(&mbar[b], sym_bytes * N + (with_tx ? N * M : 0));
-    const cf *src = a.iq + frame * a.frame_stride + a.first_sample + (long long)sym * a.L + a.cp;
+  // TMA loads of payload symbol number pg (counted over this CTA's frames) into ring slot pg & 1 (one thread)
+  auto issue_payload = [&](int pg) {
+    const int f = pg / D, d = pg - f * D;
+    if (f >= nf) return;
+    const long long frame = (long long)blockIdx.x + (long long)f * gridDim.x;
+    cf *dst = ring + (size_t)(pg & 1) * TR::BUF_ELEMS;
+    mbar_expect_tx(&mbar[pg & 1], sym_bytes * N);
+    const cf *src = a.iq + frame * a.frame_stride + a.first_sample + (long long)(a.T + d) * a.L + a.cp;
 #pragma unroll
     for (int r = 0; r < N; r++)
-      bulk_load(dst + (size_t)r * PAD, src + (long long)r * a.rx_stride, sym_bytes, &mbar[b], pol_stream);
-    if (with_tx) {
-      // the transmitted symbol indices of this OFDM symbol ride on the same mbarrier
-      const unsigned char *tsrc = a.tx_data + (frame * N * a.D + (sym - a.T)) * (long long)M;
-#pragma unroll
-      for (int s = 0; s < N; s++) bulk_load(txbuf + (b * N + s) * M, tsrc + (long long)s * a.D * M, M, &mbar[b], pol_stream);
-    }
+      bulk_load(dst + (size_t)r * PAD, src + (long long)r * a.rx_stride, sym_bytes, &mbar[pg & 1], pol_stream);
+  };
+  // Training unit number ug of this CTA: frame ug / TU, then (tx t, rx antenna r, code c) with the code fastest,
+  // i.e. OFDM symbol c * N + t of antenna r: the nac symbols that accumulate into G[r][t] follow each other.  One
+  // TMA load into landing slot ug & 1.
+  auto issue_training = [&](int ug) {
+    const int f = ug / TU, u = ug - f * TU;
+    if (f >= nf) return;
+    const long long frame = (long long)blockIdx.x + (long long)f * gridDim.x;
+    const int c = u % a.nac, r = (u / a.nac) % N, t = u / (a.nac * N);
+    mbar_expect_tx(&mbar[4 + (ug & 1)], sym_bytes);
+    bulk_load(land + (size_t)(ug & 1) * PAD, a.iq + frame * a.frame_stride + a.first_sample + (long long)(c * N + t) * a.L + a.cp +
+              (long long)r * a.rx_stride, sym_bytes, &mbar[4 + (ug & 1)], pol_stream);
   };
 
   if (tid == 0) {
@@ -173,60 +207,138 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
     mbar_init(&mbar[1], 1);
     mbar_init(&mbar[2], TR::FFT_WARPS);
     mbar_init(&mbar[3], TR::FFT_WARPS);
+    mbar_init(&mbar[4], 1);
+    mbar_init(&mbar[5], 1);
+    mbar_init(&mbar[6], TR::FFT_WARPS);
+    mbar_init(&mbar[7], DET_WARPS);
     done[0] = 0;
     done[1] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
-    if (total > 0) issue_load(0, 0, 0);
-    if (total > 1) issue_load(1, nsym > 1 ? 0 : 1, nsym > 1 ? 1 : 0);
+    issue_training(0);
+    issue_training(1);
+    issue_payload(0);
+    issue_payload(1);
   }
-  for (int i = tid; i < TR::TW_ELEMS; i += TR::THREADS) tw_s[i] = a.tw[i];
+  for (int i = tid; i < TW::CNT1; i += TR::THREADS) tw_s[i] = a.tw[TW::OFF1 + i];
   __syncthreads();
 
   if (warp < TR::FFT_WARPS) {
     // ================================ FFT warps ================================
     reg_inc<TR::FFT_REGS>();
     const int ft = tid;
-    int sym = 0;
-    for (int g = 0; g < total; g++) {
-      const int b = g & 1;
-      cf *buf = b ? buf1 : buf0;
-      const float scale = (sym >= a.T) ? a.dn : 1.0f;
-      mbar_wait(&mbar[b], (unsigned)((g >> 1) & 1));
-      // In place, stage by stage over the antennas.  The barrier between a pair's loads and its
-      // stores also orders the stores of the previous pair before the next stage's loads of that
-      // antenna (N >= 2 pairs later), so one barrier per (stage, antenna) suffices.
+    const bool q1 = (a.flags & RUB_FLAG_Q1_IDENTITY_INIT) != 0;
+    constexpr int NS2 = TW::NS2, B2 = FF::S2::B, R2 = FF::S2::P / B2;
+    const int nac = a.nac;
+    int ug = 0;               // next training unit (counted over this CTA's frames)
+    int target = TU;          // training units to have finished before the next payload symbol
+    float2 acc[FF::PTS];      // LS accumulators of this thread's 16 carriers of G[r][t], kept over the nac codes
+#pragma unroll
+    for (int i = 0; i < FF::PTS; i++) acc[i] = make_float2(0.f, 0.f);
+    // One loop serves both kinds of work (a single copy of the stage code in the instruction cache): a
+    // payload job transforms the N antennas of a ring slot in place; a training job transforms the one
+    // antenna of a landing slot, keeps the last stage's outputs in registers and accumulates them over
+    // the nac codes into G[r][t] (mimo/framing.cc:801-815).  After each payload symbol the training units
+    // of the next frame that are due are worked off.
+    int pg = -1;  // current payload symbol number (-1: prologue, the training units of the first frame)
+    while (true) {
+      const bool training = ug < target;
+      if (!training) {
+        if (++pg >= nf * D) break;
+      }
       cf v[FF::PTS], tw[FF::S1::NTW > FF::S2::NTW ? FF::S1::NTW : FF::S2::NTW];
+      const int nr = training ? 1 : N;
+      int f, c = 0, r0 = 0, t = 0;
+      cf *buf;
+      if (training) {
+        f = ug / TU;
+        const int u = ug - f * TU;
+        c = u % nac; r0 = (u / nac) % N; t = u / (nac * N);
+        buf = land + (size_t)(ug & 1) * PAD;
+        // the G scratch is free once the weights of the previous frame have been computed from it
+        if (u == 0 && f >= 1) mbar_wait(&mbar[7], (unsigned)((f - 1) & 1));
+        mbar_wait(&mbar[4 + (ug & 1)], (unsigned)((ug >> 1) & 1));
+      } else {
+        f = pg / D;
+        buf = ring + (size_t)(pg & 1) * TR::BUF_ELEMS;
+        mbar_wait(&mbar[pg & 1], (unsigned)((pg >> 1) & 1));
+      }
+      // In place, stage by stage over the job's antennas; the twiddles of a stage depend on the thread only
+      // and are read once per job.  The barrier between a pair's loads and its stores also orders the stores
+      // of the previous pair before the next stage's loads of that antenna (N >= 2 pairs later); a one-antenna
+      // job needs a barrier of its own between the stages.
 #pragma unroll 1
-      for (int r = 0; r < N; r++) {
+      for (int r = 0; r < nr; r++) {
         cf *reg = buf + (size_t)r * PAD;
         FF::S0::template load<false>(ft, reg, v);
         named_bar(1, NT);
         FF::S0::compute(ft, v, nullptr);
         FF::S0::template store<true, false>(ft, v, reg, 1.f);
       }
-      FF::S1::load_twiddles(ft, tw_s + TW::OFF1, tw);
+      FF::S1::load_twiddles(ft, tw_s, tw);
+      if (training) named_bar(1, NT);
 #pragma unroll 1
-      for (int r = 0; r < N; r++) {
+      for (int r = 0; r < nr; r++) {
         cf *reg = buf + (size_t)r * PAD;
         FF::S1::template load<true>(ft, reg, v);
         named_bar(1, NT);
         FF::S1::compute_pre(v, tw);
         FF::S1::template store<true, false>(ft, v, reg, 1.f);
       }
-      FF::S2::load_twiddles(ft, tw_s + TW::OFF2, tw);
+      FF::S2::load_twiddles(ft, a.tw + TW::OFF2, tw);
+      if (training) named_bar(1, NT);
 #pragma unroll 1
-      for (int r = 0; r < N; r++) {
+      for (int r = 0; r < nr; r++) {
         cf *reg = buf + (size_t)r * PAD;
         FF::S2::template load<true>(ft, reg, v);
         named_bar(1, NT);
+        // training: every thread has read the landing slot, refill it with the unit two ahead
+        if (training && tid == 0) issue_training(ug + 2);
         FF::S2::compute_pre(v, tw);
-        FF::S2::template store<false, true>(ft, v, reg, scale);
+        if (!training) FF::S2::template store<false, true>(ft, v, reg, a.dn);
       }
-      // Y complete: every lane's stores are ordered before lane 0's release-arrive
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&mbar[2 + b]);
-      if (++sym == nsym) sym = 0;
+      if (!training) {
+        // Y complete: every lane's stores are ordered before lane 0's release-arrive
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&mbar[2 + (pg & 1)]);
+        // training units of the next frame are spread over this frame's payload symbols from the third on
+        const int d = pg - f * D;
+        if (d == D - 1) target = (f + 2) * TU;
+        else if (d >= 2) target = (f + 1) * TU + (int)(((long long)TU * (d - 1) + (D - 3)) / (D - 2));
+        if (target > nf * TU) target = nf * TU;
+      } else {
+        // X / S1 with S1 = +-1 is a sign flip (mimo/framing.cc:809-812): the signs of this thread's carriers
+        // come as one byte per butterfly, bit t2 = carrier j + t2 * NS2
+        const float dinit = (q1 && r0 == t) ? 1.0f : 0.0f;
+#pragma unroll
+        for (int b = 0; b < B2; b++) {
+          const unsigned sb = fa.sgn8[((size_t)t * nac + c) * (M / R2) + ft + b * NT];
+#pragma unroll
+          for (int t2 = 0; t2 < R2; t2++) {
+            const int i = b * R2 + t2;
+            const unsigned neg = (sb << (31 - t2)) & 0x80000000u;
+            float2 ac = (c == 0) ? make_float2(dinit, 0.f) : acc[i];
+            ac.x = ac.x + u2f(f2u(v[i].x) ^ neg); ac.y = ac.y + u2f(f2u(v[i].y) ^ neg);
+            acc[i] = ac;
+          }
+        }
+        if (c == nac - 1) {
+          cf *Gf = fa.scratchAcc + (size_t)blockIdx.x * N * N * M + (size_t)(r0 * N + t) * M;
+#pragma unroll
+          for (int b = 0; b < B2; b++)
+#pragma unroll
+            for (int t2 = 0; t2 < R2; t2++) {
+              const int j = ft + b * NT, k = (j / NS2) * NS2 * R2 + (j % NS2) + t2 * NS2;
+              Gf[k] = mk(acc[b * R2 + t2].x, acc[b * R2 + t2].y);
+            }
+        }
+        ug++;
+        if (ug - f * TU == TU) {
+          // G(f) complete: every lane's stores are ordered before lane 0's release-arrive
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&mbar[6]);
+        }
+      }
     }
     return;
   }
@@ -234,23 +346,21 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
   // ================================ detect warps ================================
   reg_dec<TR::DET_REGS>();
   const int dtid = tid - NT, dwarp = warp - TR::FFT_WARPS;
-  cf *Wc = fa.scratchW + (size_t)blockIdx.x * N * N * M;
-  float *gc = fa.scratchG + (size_t)blockIdx.x * 2 * N * M, *ic = gc + (size_t)N * M;
   float refs[4];  // liquid ref[k] = 2^k * alpha, most significant first
 #pragma unroll
   for (int i = 0; i < 4; i++) refs[i] = (i < MB) ? (float)(1u << (MB - 1 - i)) * dc.alpha : 0.f;
   const int koff = dwarp * 64 + 2 * lane;                // first carrier of this lane in block kb = 0
   constexpr int KSTEP = 64 * DET_WARPS;                  // carrier distance between a warp's blocks
-  unsigned char *slot0 = stage_base + (size_t)(dwarp * 2) * stage_stride;
-  // per-lane error counts, 16 bits per stream: bit errors in eb, symbol errors in es
-  unsigned long long eb = 0, es = 0;
+  unsigned char *slot0 = stage_base + (size_t)(dwarp * 2) * stage_stride;  // this warp's two LLR staging slots
+  // per-lane error counts, 16 bits per stream (streams 0,1 in word 0; 2,3 in word 1)
+  unsigned eb0 = 0, eb1 = 0, es0 = 0, es1 = 0;
   // the 16-bit fields must survive the warp sum: flush before 32 lanes x bit errors can reach 65536
   const int flush_every = max(1, 2047 / (KPW * 2 * Q));
   int since_flush = 0;
   auto flush_counts = [&](int nsyms_flushed) {
-    const unsigned b0 = __reduce_add_sync(0xffffffffu, (unsigned)eb), b1 = __reduce_add_sync(0xffffffffu, (unsigned)(eb >> 32));
-    const unsigned s0 = __reduce_add_sync(0xffffffffu, (unsigned)es), s1 = __reduce_add_sync(0xffffffffu, (unsigned)(es >> 32));
-    eb = 0; es = 0;
+    const unsigned b0 = __reduce_add_sync(0xffffffffu, eb0), b1 = __reduce_add_sync(0xffffffffu, eb1);
+    const unsigned s0 = __reduce_add_sync(0xffffffffu, es0), s1 = __reduce_add_sync(0xffffffffu, es1);
+    eb0 = eb1 = es0 = es1 = 0;
     if (lane < N && a.counters) {
       const unsigned bw = (lane & 2) ? b1 : b0, sw = (lane & 2) ? s1 : s0;
       atomicAdd(&a.counters[lane * 4 + 0], (unsigned long long)((bw >> (16 * (lane & 1))) & 0xffffu));
@@ -260,113 +370,96 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
     }
   };
 
-  int fl = 0, sym = 0;
-  for (int g = 0; g < total; g++) {
-    const int b = g & 1;
-    const long long frame = (long long)blockIdx.x + (long long)fl * gridDim.x;
-    const cf *buf = b ? buf1 : buf0;
-    const bool payload = sym >= a.T;
-    const cf *wp = Wc + koff;         // W[s][0][k] of the current task (this lane's carriers)
-    const float *gp = gc + koff;      // gain[s][k]; isig follows N*M floats later
-    TaskRegs<N> w;
-    auto load_w = [&]() {
-#pragma unroll
-      for (int r = 0; r < N; r++) w.w[r] = ld_hint4(wp + r * M, pol_keep);
-      w.g = ld_hint2(gp, pol_keep);
-      w.is = ld_hint2(gp + N * M, pol_keep);
-    };
-    if (payload) load_w();  // W of the first task: requested before Y is needed
-    if (sym == 0 && fl > 0) named_bar(2, DET_THREADS);  // every warp is done reading the previous frame's W
-    mbar_wait(&mbar[2 + b], (unsigned)((g >> 1) & 1));
-    // This warp's last generic-proxy access to the ring slot is done.  The last warp to say so refills the
-    // slot with the symbol two ahead.
-    auto release_buf = [&]() {
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        if (atom_add_acq_rel_smem(&done[b], 1u) == (unsigned)(DET_WARPS - 1)) {
-          done[b] = 0;
-          if (g + 2 < total) {
-            int s2 = sym + 2, f2 = fl;
-            if (s2 >= nsym) { s2 -= nsym; f2++; }
-            issue_load(b, f2, s2);
-          }
-        }
-      }
-    };
-    if (!payload) {
-      // ---------------- LS accumulate (mimo/framing.cc:801-815) ----------------
-      const int c = sym / N, t = sym % N;
-      const bool q1 = (a.flags & RUB_FLAG_Q1_IDENTITY_INIT) != 0;
-      constexpr int LS_IT = (N * M / 2) / DET_THREADS;
-      float4 accv[LS_IT];
-#pragma unroll
-      for (int i = 0; i < LS_IT; i++) {
-        const int e = dtid + i * DET_THREADS, r = e / (M / 2), k = 2 * (e % (M / 2));
-        if (c == 0) { const float d = (q1 && r == t) ? 1.0f : 0.0f; accv[i] = make_float4(d, 0.f, d, 0.f); }
-        else accv[i] = ld_hint4(Wc + (size_t)(r * N + t) * M + k, pol_keep);
-      }
-#pragma unroll
-      for (int i = 0; i < LS_IT; i++) {
-        const int e = dtid + i * DET_THREADS, r = e / (M / 2), k = 2 * (e % (M / 2));
-        const float4 x = *reinterpret_cast<const float4 *>(buf + (size_t)r * PAD + k);
-        const float2 sg = __ldg(reinterpret_cast<const float2 *>(a.sgn + ((size_t)t * a.nac + c) * M + k));
-        float4 acc = accv[i];
-        acc.x = acc.x + x.x * sg.x; acc.y = acc.y + x.y * sg.x;
-        acc.z = acc.z + x.z * sg.y; acc.w = acc.w + x.w * sg.y;
-        st_hint4(Wc + (size_t)(r * N + t) * M + k, acc, pol_keep);
-      }
-      release_buf();
-      if (sym == a.T - 1) {
-        // ---------------- weights (mimo/framing.cc:817-832) ----------------
-        named_bar(2, DET_THREADS);
+  int pg = 0;
+  for (int f = 0; f < nf; f++) {
+    const long long frame = (long long)blockIdx.x + (long long)f * gridDim.x;
+    cf *Wc = fa.scratchW + (size_t)blockIdx.x * N * N * M;
+    const cf *Gc = fa.scratchAcc + (size_t)blockIdx.x * N * N * M;
+    float *gc = fa.scratchG + (size_t)blockIdx.x * 2 * N * M, *ic = gc + (size_t)N * M;
+    // ---------------- weights (mimo/framing.cc:817-832) ----------------
+    mbar_wait(&mbar[6], (unsigned)(f & 1));  // G(f) is complete (written by the FFT warps)
+    if (f > 0) named_bar(2, DET_THREADS);     // every detect warp is done reading the previous frame's W
 #pragma unroll 1
-        for (int k = dtid; k < M; k += DET_THREADS) {
-          cf G[N * N], W[N * N];
-          float gain[N], isig[N];
+    for (int k = dtid; k < M; k += DET_THREADS) {
+      cf G[N * N], W[N * N];
+      float gain[N], isig[N];
 #pragma unroll
-          for (int e = 0; e < N * N; e++) {
-            const float2 t2 = ld_hint2(Wc + (size_t)e * M + k, pol_keep);
-            G[e] = cscale(mk(t2.x, t2.y), a.s_ls);
-          }
-          if (a.G) {
-#pragma unroll
-            for (int e = 0; e < N * N; e++) a.G[(frame * N * N + e) * M + k] = G[e];
-          }
-          compute_weights<N>(fa.wm, G, W, gain, isig);
-#pragma unroll
-          for (int e = 0; e < N * N; e++) st_hint2(Wc + (size_t)e * M + k, make_float2(W[e].x, W[e].y), pol_keep);
-#pragma unroll
-          for (int s = 0; s < N; s++) { st_hint1(gc + (size_t)s * M + k, gain[s], pol_keep); st_hint1(ic + (size_t)s * M + k, isig[s], pol_keep); }
-        }
-        named_bar(2, DET_THREADS);  // W complete before any warp reads it
+      for (int e = 0; e < N * N; e++) {
+        const float2 t2 = ld_hint2(Gc + (size_t)e * M + k, pol_stream);
+        G[e] = cscale(mk(t2.x, t2.y), a.s_ls);
       }
-    } else {
-      // ---------------- detect + demap + count ----------------
-      long long o = (frame * N * a.D + (sym - a.T)) * (long long)M + koff;  // stream 0, block 0, this lane
-      const long long DM = (long long)a.D * M;
-      const unsigned char *txl = txbuf + b * N * M + koff;
+      if (a.G) {
+#pragma unroll
+        for (int e = 0; e < N * N; e++) a.G[(frame * N * N + e) * M + k] = G[e];
+      }
+      compute_weights<N>(fa.wm, G, W, gain, isig);
+#pragma unroll
+      for (int e = 0; e < N * N; e++) st_hint2(Wc + (size_t)e * M + k, make_float2(W[e].x, W[e].y), pol_keep);
+#pragma unroll
+      for (int s = 0; s < N; s++) { st_hint1(gc + (size_t)s * M + k, gain[s], pol_keep); st_hint1(ic + (size_t)s * M + k, isig[s], pol_keep); }
+    }
+    // the G scratch has been consumed: the FFT warps may start on the frame after this one
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&mbar[7]);
+    named_bar(2, DET_THREADS);  // W complete before any warp reads it; every warp is past the previous frame
+
+    // ---------------- detect + demap + count, payload symbol by payload symbol ----------------
+#pragma unroll 1
+    for (int d = 0; d < D; d++, pg++) {
+      const int b = pg & 1;
+      const cf *buf = ring + (size_t)b * TR::BUF_ELEMS;
+      const cf *wp = Wc + koff;         // W[s][0][k] of the current task (this lane's carriers)
+      const float *gp = gc + koff;      // gain[s][k]; isig follows N*M floats later
+      long long o = (frame * N * D + d) * (long long)M + koff;  // output index: stream 0, block 0, this lane
+      const long long DM = (long long)D * M;
+      // byte offset of the task's 64-carrier block in the packed-bits output (Q bytes per 8 carriers); the
+      // block's LLRs start 32 times as far into the LLR output
+      long long bo = ((frame * N * D + d) * (long long)M + dwarp * 64) / 8 * Q;
+      const long long bo_s = DM / 8 * Q, bo_k = (long long)KSTEP / 8 * Q - (N - 1) * bo_s;
+      TaskRegs<N> w;
+      unsigned txv = 0;  // transmitted symbols of the two carriers of the task
+      auto load_w = [&]() {
+#pragma unroll
+        for (int r = 0; r < N; r++) w.w[r] = ld_hint4(wp + r * M, pol_keep);
+        w.g = ld_hint2(gp, pol_keep);
+        w.is = ld_hint2(gp + N * M, pol_keep);
+        if (a.tx_data) txv = ld_hint_u16(a.tx_data + o, pol_stream);
+      };
+      load_w();  // first task: requested before Y is needed
+      if (a.tx_data && lane < KPW * N) {
+        // the reference symbols of this warp's tasks of the NEXT payload symbol: pull their lines into L2 now so
+        // that the 2-byte loads riding with the W loads never wait for HBM
+        const unsigned char *tp = a.tx_data + (o - 2 * lane) + (long long)(lane % N) * DM + (lane / N) * KSTEP;
+        if (d == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(tp));
+        if (d + 1 < D) asm volatile("prefetch.global.L2 [%0];" ::"l"(tp + M));
+      }
+      mbar_wait(&mbar[2 + b], (unsigned)((pg >> 1) & 1));
       int it = 0;
 #pragma unroll 1
       for (int kb = 0; kb < KPW; kb++) {
         float4 y4[N];
 #pragma unroll
         for (int r = 0; r < N; r++) y4[r] = *reinterpret_cast<const float4 *>(buf + (size_t)r * PAD + koff + kb * KSTEP);
-        unsigned long long txp = 0;  // reference symbols of the N streams, 16 bits each
-        if (a.tx_data) {
-#pragma unroll
-          for (int s = 0; s < N; s++)
-            txp |= (unsigned long long)*reinterpret_cast<const unsigned short *>(txl + s * M + kb * KSTEP) << (16 * s);
+        if (kb == KPW - 1) {
+          // This warp's last generic-proxy access to the ring slot is done (Y is in registers).  The last
+          // warp to say so refills the slot with the payload symbol two ahead.
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0 && atom_add_acq_rel_smem(&done[b], 1u) == (unsigned)(DET_WARPS - 1)) {
+            done[b] = 0;
+            issue_payload(pg + 2);
+          }
         }
-        if (kb == KPW - 1) release_buf();  // Y and the reference symbols are in registers
 #pragma unroll 1
         for (int s = 0; s < N; s++, it++) {
           cf z0, z1;
           const float2 is = w.is;
+          const unsigned tx2 = txv;
+          const long long oc = o, boc = bo;
           ws_dot<N>(w, y4, z0, z1);
           // W of the next task lands in the registers the products just released
-          if (s + 1 < N) { wp += N * M; gp += M; }
-          else { wp += KSTEP - (N - 1) * N * M; gp += KSTEP - (N - 1) * M; }
+          if (s + 1 < N) { wp += N * M; gp += M; o += DM; bo += bo_s; }
+          else { wp += KSTEP - (N - 1) * N * M; gp += KSTEP - (N - 1) * M; o += (long long)KSTEP - (N - 1) * DM; bo += bo_k; }
           if (it + 1 < KPW * N) load_w();
           unsigned char *slot = slot0 + (it & 1) * stage_stride;
           if (a.llr) {
@@ -374,26 +467,26 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
             if (lane == 0) bulk_wait_read<1>();
             __syncwarp();
           }
-          const unsigned rx2 = ws_demap<MB>(a, dc, refs, z0, z1, is, o, reinterpret_cast<float *>(slot) + lane * 2 * Q, pol_stream);
+          const unsigned rx2 = ws_demap<MB>(a, dc, refs, z0, z1, is, oc, reinterpret_cast<float *>(slot) + lane * 2 * Q,
+                                            reinterpret_cast<unsigned short *>(a.bits + boc + (lane >> 2) * Q), pol_stream, lane);
           if (a.llr) {
             fence_async_smem();
             __syncwarp();
             if (lane == 0) {
-              bulk_store(a.llr + (o - 2 * lane) * Q, slot, (unsigned)(64 * Q * 4), pol_stream);
+              bulk_store(reinterpret_cast<unsigned char *>(a.llr) + boc * 32, slot, (unsigned)(64 * Q * 4), pol_stream);
               bulk_commit();
             }
           }
           if (a.tx_data) {
-            const unsigned x = rx2 ^ ((unsigned)(txp >> (16 * s)) & 0xffffu);
-            eb += (unsigned long long)__popc(x) << (16 * s);
-            es += (unsigned long long)(((x & 0xffu) != 0u ? 1u : 0u) + ((x >> 8) != 0u ? 1u : 0u)) << (16 * s);
+            const unsigned x = rx2 ^ tx2;
+            const unsigned vb = (unsigned)__popc(x) << (16 * (s & 1));
+            const unsigned vs = (((x & 0xffu) != 0u ? 1u : 0u) + ((x >> 8) != 0u ? 1u : 0u)) << (16 * (s & 1));
+            if (s & 2) { eb1 += vb; es1 += vs; } else { eb0 += vb; es0 += vs; }
           }
-          o += (s + 1 < N) ? DM : (long long)KSTEP - (N - 1) * DM;
         }
       }
-      if (a.tx_data && (++since_flush == flush_every || sym == nsym - 1)) { flush_counts(since_flush); since_flush = 0; }
+      if (a.tx_data && (++since_flush == flush_every || d == D - 1)) { flush_counts(since_flush); since_flush = 0; }
     }
-    if (++sym == nsym) { sym = 0; fl++; }
   }
   if (lane == 0) bulk_wait_all();
 }

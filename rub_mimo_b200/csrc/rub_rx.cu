@@ -85,6 +85,9 @@ struct rub_rx {
   // fused scratch
   cf *d_fW = nullptr;
   float *d_fG = nullptr;
+  cf *d_fAcc = nullptr;             // warp-specialised kernel: LS estimate of the next frame, per CTA
+  unsigned char *d_sgn8 = nullptr;  // warp-specialised kernel: packed access-code signs
+  std::vector<float> sgn_host;      // access-code signs [tx][code][M]
   int fused_grid = 0;
   bool ws = false;  // the warp-specialised fused kernel (rub_kernels_ws.cuh) serves this configuration
   size_t fused_smem = 0;
@@ -111,8 +114,8 @@ struct rub_rx {
 
 // fused kernels live in their own translation units (rub_fused.cu, rub_ws.cu)
 static rub_status fused_prepare_dispatch(rub_rx *h, size_t *smem, int *grid) {
-  const char *e = getenv("RUB_FUSED_WS");  // development switch: RUB_FUSED_WS=1 selects the warp-specialised kernel
-  h->ws = (e && e[0] == '1') && ws_has_instance(h->h.log2M, h->h.N);
+  const char *e = getenv("RUB_FUSED_WS");  // development switch: RUB_FUSED_WS=0 keeps the monolithic kernel
+  h->ws = !(e && e[0] == '0') && ws_has_instance(h->h.log2M, h->h.N);
   int occ = 0;
   cudaError_t ce = cudaErrorInvalidValue;
   if (h->ws) {
@@ -214,6 +217,7 @@ extern "C" rub_status rub_rx_create(rub_rx **out, const rub_config *cfg, const f
     }
     sgn[i] = isnull ? 0.f : re;
   }
+  h->sgn_host = sgn;
   CT(cudaMalloc(&h->d_sgn, sizeof(float) * sgn.size()));
   CT(cudaMemcpy(h->d_sgn, sgn.data(), sizeof(float) * sgn.size(), cudaMemcpyHostToDevice));
   {
@@ -244,7 +248,7 @@ extern "C" void rub_rx_destroy(rub_rx *h) {
   if (h->s_comm) cudaStreamSynchronize(h->s_comm);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   cudaFree(h->d_tw); cudaFree(h->d_occ); cudaFree(h->d_sgn); cudaFree(h->d_null); cudaFree(h->d_s1); cudaFree(h->d_s0); cudaFree(h->d_sync);
-  cudaFree(h->d_scratch); cudaFree(h->d_fW); cudaFree(h->d_fG); cudaFree(h->d_counters); cudaFree(h->d_pipe);
+  cudaFree(h->d_scratch); cudaFree(h->d_fW); cudaFree(h->d_fG); cudaFree(h->d_fAcc); cudaFree(h->d_sgn8); cudaFree(h->d_counters); cudaFree(h->d_pipe);
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);
   for (auto &e : h->pev) if (e) cudaEventDestroy(e);
   cudaFree(h->d_snap);
@@ -425,8 +429,17 @@ static rub_status run_fused(rub_rx *h, const ChainArgs &a, uint32_t n_frames, bo
     if (st) { h->fused_unfit = st == RUB_ERR_UNSUPPORTED; return st; }
     h->fused_grid = grid;
     h->fused_smem = smem;
+    // per-CTA scratch: G -> W in place, gain, isig (re-read D times per frame: L2 resident)
     CUDA_TRY(cudaMalloc(&h->d_fW, (size_t)grid * c.N * c.N * c.M * sizeof(cf)));
     CUDA_TRY(cudaMalloc(&h->d_fG, (size_t)grid * 2 * c.N * c.M * sizeof(float)));
+    if (h->ws) {
+      // the warp-specialised kernel estimates frame f+1 while frame f is detected
+      CUDA_TRY(cudaMalloc(&h->d_fAcc, (size_t)grid * c.N * c.N * c.M * sizeof(cf)));
+      std::vector<unsigned char> s8(ws_sign_bytes(c.log2M, c.N, c.nac));
+      ws_pack_signs(c.log2M, c.N, c.nac, h->sgn_host.data(), s8.data());
+      CUDA_TRY(cudaMalloc(&h->d_sgn8, s8.size()));
+      CUDA_TRY(cudaMemcpy(h->d_sgn8, s8.data(), s8.size(), cudaMemcpyHostToDevice));
+    }
     h->fused_ready = true;
   }
   const size_t smem = h->fused_smem;
@@ -435,6 +448,8 @@ static rub_status run_fused(rub_rx *h, const ChainArgs &a, uint32_t n_frames, bo
   fa.a.n_frames = (int)n_frames;
   fa.scratchW = h->d_fW;
   fa.scratchG = h->d_fG;
+  fa.scratchAcc = h->d_fAcc;
+  fa.sgn8 = h->d_sgn8;
   fa.llr_stage_bytes = 256 * (int)c.q;
   fa.wm = h->wm;
   const int grid = (int)std::min<uint32_t>((uint32_t)h->fused_grid, n_frames);

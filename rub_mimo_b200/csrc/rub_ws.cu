@@ -46,6 +46,17 @@ cudaError_t ws_prepare(uint32_t l2, uint32_t N, uint32_t q, size_t *smem, int *o
 #undef X
   return cudaErrorInvalidValue;
 }
+void ws_pack_signs(uint32_t l2, uint32_t N, uint32_t nac, const float *sgn, unsigned char *out) {
+#define X(L, NN) if (l2 == L && N == NN) { ws_pack_signs<L>((int)N, (int)nac, sgn, out); return; }
+  RUB_WS_LIST(X)
+#undef X
+}
+size_t ws_sign_bytes(uint32_t l2, uint32_t N, uint32_t nac) {
+#define X(L, NN) if (l2 == L && N == NN) return (size_t)N * nac * (Fft<L>::M / (Fft<L>::S2::P / Fft<L>::S2::B));
+  RUB_WS_LIST(X)
+#undef X
+  return 0;
+}
 void ws_launch(uint32_t l2, uint32_t N, int grid, size_t smem, cudaStream_t st, const FusedArgs &fa, const DemapConst &dc) {
 #define X(L, NN) if (l2 == L && N == NN) { launch<L, NN>(grid, smem, st, fa, dc); return; }
   RUB_WS_LIST(X)
