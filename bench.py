@@ -2,16 +2,23 @@
 """bench.py — MIMO-OFDM receive throughput on B200 (BASELINE.json metric).
 
   python bench.py --gpus N --steps K --warmup W            our CUDA path (C-ABI library)
-  python bench.py --impl reference --gpus N --steps K ...  the reference's CPU algorithm
-                                                           (oracle port, all host cores)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's CPU algorithm on the host cores
 
 A "step" is one pass of the receive hot path (CP strip -> FFT -> LS estimate -> MMSE -> demap ->
-LLR/bits -> error count) over one batch of synthetic pre-aligned frames.  Workload = C3
+LLR/bits -> error count) over one batch of synthetic pre-aligned frames.  Default workload = C3
 (SURVEY.md 8d target config): 4x4, 2048 subcarriers, cp 152, 64-QAM, MMSE, nac=2, D=14,
-1024 frames per GPU (weak scaling: each rank owns a contiguous frame range, the only exchange
-is one ncclAllReduce of the 4*N uint64 error counters per step).
+1024 frames per GPU (weak scaling: each rank owns a contiguous frame range; the only exchange is
+one ncclAllReduce of the 4*N uint64 error counters per step, issued on a side stream).
+
+  --workload C2 | C4   the other BASELINE configurations (same code path, other geometry)
+  --workload REF       the reference's own geometry (2x2 / 2048 / cp 152 / 20 access codes / 1000
+                       QPSK symbols / ZF, mimo/config.h:65-66, :92, :104): a raw capture through
+                       rub_rx_process_capture on the GPU arm and through the reference's own
+                       framing.cc (oracle/_ref) on the --impl reference arm.
 """
 import argparse
+import ctypes as C
+import hashlib
 import json
 import os
 import subprocess
@@ -25,10 +32,17 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    "C3": dict(preset="C3", frames_per_gpu=1024, unique=64, label="C3 4x4/2048sc/cp152/64-QAM/MMSE+LLR nac2 D14"),
-    "C2": dict(preset="C2", frames_per_gpu=4096, unique=128, label="C2 2x2/1024sc/cp72/16-QAM/ZF nac2 D14"),
-    "C4": dict(preset="C4", frames_per_gpu=256, unique=16, label="C4 8x8/4096sc/cp288/256-QAM/MMSE comb-interp nac2 D14"),
+    "C3": dict(preset="C3", frames_per_gpu=1024, unique=64, label="C3 4x4/2048sc/cp152/64-QAM/MMSE+LLR nac2 D14",
+               geom=dict(M=2048, cp=152, N=4, nac=2, D=14, q=6, detector=1, flags_unbiased=True, n_taps=8, snr_db=30.0, seed=0xC3)),
+    "C2": dict(preset="C2", frames_per_gpu=4096, unique=128, label="C2 2x2/1024sc/cp72/16-QAM/ZF nac2 D14",
+               geom=dict(M=1024, cp=72, N=2, nac=2, D=14, q=4, detector=0, flags_unbiased=False, n_taps=1, snr_db=25.0, seed=0xC2)),
+    "C4": dict(preset="C4", frames_per_gpu=256, unique=16, label="C4 8x8/4096sc/cp288/256-QAM/MMSE comb-interp nac2 D14",
+               geom=dict(M=4096, cp=288, N=8, nac=2, D=14, q=8, detector=1, flags_unbiased=True, n_taps=16, snr_db=38.0, seed=0xC4,
+                         estimator=1)),
+    "REF": dict(label="REF 2x2/2048sc/cp152/QPSK/ZF nac20 D1000 raw capture (the reference's default geometry)",
+                geom=dict(M=2048, cp=152, N=2, nac=20, D=1000, q=2)),
 }
+KERNEL_SOURCES = ["rub_kernels_ws.cuh", "rub_kernels_fused.cuh", "rub_kernels_staged.cuh", "rub_arith.cuh", "rub_fft.cuh"]
 
 
 def _peaks():
@@ -39,12 +53,25 @@ def _peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def _traffic():
+def kernel_source_sha():
+    h = hashlib.sha256()
+    for n in KERNEL_SOURCES:
+        with open(os.path.join(ROOT, "rub_mimo_b200", "csrc", n), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def _traffic(kernel, workload):
+    """DRAM bytes per launch of the dominant kernel from the ncu capture kept under profiles/ — only when that
+    capture was taken from the same kernel sources and workload (tools/ncu_traffic.py stamps both)."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f)
+            t = json.load(f)
+        if t.get("kernel") == kernel and t.get("workload") == workload and t.get("source_sha") == kernel_source_sha():
+            return t.get("dram_bytes_per_launch")
     except Exception:
-        return None
+        pass
+    return None
 
 
 class ClockSampler:
@@ -61,7 +88,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -113,60 +140,152 @@ def _bind_to_gpu_cpus(dev_index):
     return None
 
 
-def metric_values(cfg, frames, seconds):
-    samples = frames * cfg.D * cfg.N * (cfg.M + cfg.cp_len)
-    det = frames * cfg.D * cfg.Mo
-    return samples / seconds / 1e6, det / seconds
+def samples_per_frame(g):
+    return g["D"] * g["N"] * (g["M"] + g["cp"])
 
 
 # ------------------------------------------------------------------------ CPU legs -----
-def cpu_oracle_rate(cfg, S1, iq, tx, n_threads, reps=3):
-    """Times the oracle (plain-C port of the reference algorithm) on `n_threads` host threads."""
+# Only these functions execute anything under oracle/ (test infrastructure): the cpu_baseline leg
+# of our arm and the --impl reference arm.  One timing method for both: mean wall time of `reps`
+# passes after `warmup` untimed ones, all host cores (OpenMP over frames).
+def cpu_port_time(oc, S1, iq, tx, cores, reps, warmup):
     from oracle import orc
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from util import to_orc
-    oc = to_orc(cfg)
-    best = None
+    for _ in range(warmup):
+        orc.rx_batch(oc, S1, iq, tx_data=tx, want=("eq", "llr", "bits"), n_threads=cores)
+    ts = []
     for _ in range(reps):
         t0 = time.perf_counter()
-        orc.rx_batch(oc, S1, iq, tx_data=tx, want=("eq", "llr", "bits"), n_threads=n_threads)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return best
+        orc.rx_batch(oc, S1, iq, tx_data=tx, want=("eq", "llr", "bits"), n_threads=cores)
+        ts.append(time.perf_counter() - t0)
+    return float(np.mean(ts)), ts
+
+
+def cpu_sample_frames(cores, frames_per_gpu):
+    return int(max(cores, min(frames_per_gpu, 4 * cores)))
+
+
+def ref_capture(g, seed=0xC6, snr_db=30.0):
+    """A default-geometry capture built with the REFERENCE's own framegen (oracle/_ref) when it is there,
+    else with the oracle's: lead-in zeros, S0 + 2*nac access codes + D QPSK packets, flat 2x2 channel, AWGN."""
+    from oracle import orc
+    M, cp, nac, D, q = g["M"], g["cp"], g["nac"], g["D"], g["q"]
+    L = M + cp
+    rng = np.random.default_rng(seed)
+    so = os.path.join(ROOT, "oracle", "_ref", "libref_framing.so")
+    lib = C.CDLL(so) if os.path.exists(so) else None
+    p = np.zeros(M, np.uint8)
+    if lib is not None:
+        n = [C.c_uint(), C.c_uint(), C.c_uint()]
+        lib.ref_default_sctype(C.c_uint(M), p.ctypes.data_as(C.c_void_p), C.byref(n[0]), C.byref(n[1]), C.byref(n[2]))
+    else:
+        p = orc.init_default_sctype(M, True, True)
+    Mo = int(np.count_nonzero(p))
+    tab = orc.modulate_table(q)
+    data = rng.integers(0, 1 << q, size=(D, 2, Mo), dtype=np.uint8)
+    syms = np.ascontiguousarray(tab[data])
+    tx = np.zeros((2, (nac * 2 + 1 + D) * L), np.complex64)
+    if lib is not None:
+        n = lib.ref_framegen(C.c_uint(M), C.c_uint(cp), C.c_uint(nac), p.ctypes.data_as(C.c_void_p),
+                             syms.ctypes.data_as(C.c_void_p), C.c_uint(D), C.c_uint(Mo), tx.ctypes.data_as(C.c_void_p))
+        assert n == tx.shape[1]
+    else:
+        oc = orc.Config(M, cp, 2, nac, D, q, sctype=p)
+        S0, s0 = orc.init_S0(p, M, orc.Mseq(12, 0o10123, 1))
+        s1 = np.stack([orc.init_S1(p, M, nac, orc.Mseq(13, g1, 1))[1] for g1 in (0o20033, 0o20047)])
+        pre = orc.write_sync_words(oc, s0, s1)
+        tx[:, :pre.shape[1]] = pre
+        for d in range(D):
+            tx[:, pre.shape[1] + d * L: pre.shape[1] + (d + 1) * L] = orc.assemble_mimo_packet(oc, syms[d])
+    H = np.array([[1, 0.5], [0.5j, 1]], np.complex64)
+    lead = (nac * 2 + 1) * L
+    cap = np.zeros((2, lead + tx.shape[1] + 4 * L), np.complex64)
+    cap[:, lead:lead + tx.shape[1]] = H @ tx
+    nv = float(np.mean(np.abs(cap[:, lead:lead + tx.shape[1]]) ** 2)) / 10.0 ** (snr_db / 10.0)
+    cap += ((rng.standard_normal(cap.shape) + 1j * rng.standard_normal(cap.shape)) * np.sqrt(nv / 2)).astype(np.complex64)
+    return p, Mo, np.ascontiguousarray(cap), data, lib
+
+
+class _RefSyncResult(C.Structure):
+    _fields_ = [("state", C.c_int32), ("sync_index", C.c_uint64), ("num_samples_processed", C.c_uint64),
+                ("plateau_start", C.c_uint64 * 2), ("plateau_end", C.c_uint64 * 2), ("symbols", C.c_uint32)]
 
 
 def run_reference(args):
-    """--impl reference: the reference's own framing.cc only builds against stand-in headers
-    (oracle/_ref; FFTW3f, liquid-dsp, VOLK, UHD, Boost, GNU Radio are absent), is 2x2 / ZF only and
-    sample-serial, so it pins parity (tests/test_ref_fixtures.py) but cannot run this workload: this
-    arm times the oracle port of its algorithm (own radix FFT instead of FFTW) on all host cores,
-    on a bounded sample."""
+    """--impl reference.  Never loads the product library.
+    REF workload: the reference's own mimo/framing.cc (oracle/_ref/libref_framing.so, compiled where it lies
+    against stand-in headers; one host thread, as mimo/main.cc's receive loop) on a default-geometry capture;
+    kind "reference".  C2/C3/C4: the reference's code is 2x2 / ZF / sample-serial and cannot run them, so the
+    oracle port of its algorithm runs on all host cores (OpenMP over frames); kind "port"."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import rub_mimo_b200 as rub
+    from oracle import orc, synth
     wl = WORKLOADS[args.workload]
-    cfg = rub.preset(wl["preset"])
+    g = wl["geom"]
     cores = os.cpu_count() or 1
-    nf = max(cores, min(wl["frames_per_gpu"], 8 * cores))  # bounded sample, ~seconds of CPU work
-    syn = dict(rub.PRESET_SYNTH[wl["preset"]]); seed = syn.pop("seed")
-    S1, s1 = rub.default_S1(cfg)
-    iq, tx, nv = rub.synth_frames(cfg, nf, seed, S1=S1, s1=s1, **syn)
-    cfg = cfg.with_noise_var(nv)
-    for _ in range(args.warmup):
-        cpu_oracle_rate(cfg, S1, iq, tx, cores, reps=1)
-    times = [cpu_oracle_rate(cfg, S1, iq, tx, cores, reps=1) for _ in range(args.steps)]
-    sec = float(np.mean(times))
-    msps, det = metric_values(cfg, nf, sec)
+    if args.workload == "REF":
+        p, Mo, cap, data, lib = ref_capture(g)
+        n = cap.shape[1]
+        if lib is not None:
+            def one():
+                r = _RefSyncResult()
+                G = np.zeros((g["M"], 2, 2), np.complex64)
+                eq = np.zeros((2, g["D"] + 8, Mo), np.complex64)
+                lib.ref_framesync(C.c_uint(g["M"]), C.c_uint(g["cp"]), C.c_uint(g["nac"]), p.ctypes.data_as(C.c_void_p),
+                                  cap[0].ctypes.data_as(C.c_void_p), cap[1].ctypes.data_as(C.c_void_p), C.c_uint64(n),
+                                  C.c_uint(4096), C.byref(r), G.ctypes.data_as(C.c_void_p), eq.ctypes.data_as(C.c_void_p),
+                                  C.c_uint(g["D"] + 8), C.c_uint(Mo))
+                assert r.state == 3, "the reference did not reach STATE_MIMO"
+                return r.symbols
+            kind, used = "reference", 1
+            note = "oracle/_ref/libref_framing.so = the reference's own mimo/framing.cc (stand-in FFT/VOLK/liquid), one host thread like mimo/main.cc"
+        else:
+            oc = orc.Config(g["M"], g["cp"], 2, g["nac"], g["D"], g["q"], sctype=p, flags=1)
+            S0, _ = orc.init_S0(p, g["M"], orc.Mseq(12, 0o10123, 1))
+            S1 = np.stack([orc.init_S1(p, g["M"], g["nac"], orc.Mseq(13, g1, 1))[0] for g1 in (0o20033, 0o20047)])
+            def one():
+                r = orc.framesync_execute(oc, S0, S1, cap)
+                assert r["rc"] == 0
+                return r["symbols_decoded"]
+            kind, used = "port", 1
+            note = "oracle/_ref absent on this box: the oracle's restatement of the receive loop, one host thread"
+        for _ in range(min(args.warmup, 1)):
+            one()
+        steps = max(1, min(args.steps, 5))
+        ts = []
+        for _ in range(steps):
+            t0 = time.perf_counter(); one(); ts.append(time.perf_counter() - t0)
+        sec = float(np.mean(ts))
+        msps = 2 * n / sec / 1e6
+        sample = f"one {n}-sample 2-stream capture (1 burst, {g['D']} OFDM symbols) per step"
+        cfgd = {"workload": wl["label"], "capture_samples_per_stream": int(n), "note": note}
+        nf = 1
+    else:
+        nf = cpu_sample_frames(cores, wl["frames_per_gpu"])
+        flags = 0x2 if g["flags_unbiased"] else 0  # ORC flag MMSE_UNBIASED (same value as RUB_FLAG_MMSE_UNBIASED)
+        oc = orc.Config(g["M"], g["cp"], g["N"], g["nac"], g["D"], g["q"], detector=g["detector"],
+                        estimator=g.get("estimator", 0), flags=flags)
+        S1, iq, tx, nv = synth.synth_frames(oc, min(nf, 32), g["seed"], n_taps=g["n_taps"], snr_db=g["snr_db"])
+        reps = (nf + iq.shape[0] - 1) // iq.shape[0]
+        iq = np.tile(iq, (reps, 1, 1))[:nf]
+        tx = np.tile(tx, (reps, 1, 1, 1))[:nf]
+        oc = orc.Config(g["M"], g["cp"], g["N"], g["nac"], g["D"], g["q"], detector=g["detector"],
+                        estimator=g.get("estimator", 0), flags=flags, noise_var=nv)
+        if g.get("estimator", 0) == 1:
+            raise SystemExit("the oracle-side generator has no comb-pilot preamble: use --workload C3 or C2 for the reference arm")
+        sec, ts = cpu_port_time(oc, S1, iq, tx, cores, max(1, args.steps), args.warmup)
+        msps = nf * samples_per_frame(g) / sec / 1e6
+        kind, used = "port", cores
+        sample = f"{nf} frames of the {args.workload} workload per step, OpenMP over frames"
+        cfgd = {"workload": wl["label"], "frames_per_step": nf,
+                "note": "the reference's own framing.cc (oracle/_ref) is 2x2 / ZF / sample-serial and cannot run this workload "
+                        "(bench.py --workload REF times it on its own geometry); this arm times the oracle port of its algorithm"}
     line = {
         "impl": "reference", "metric": "rx_msamples_per_s", "value": msps, "unit": "Msamples/s",
-        "detections_per_s": det, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["label"], "frames_per_step": nf,
-                   "note": "the reference's own framing.cc (oracle/_ref, built against stand-in headers) is 2x2 / ZF only and pins parity; it cannot run this 4x4 MMSE workload, so the oracle port (own radix FFT, no FFTW) is timed"},
-        "cpu_baseline": {"value": msps, "unit": "Msamples/s", "cores": cores, "kind": "port",
-                         "sample": f"{nf} frames of the {wl['preset']} workload per step, OpenMP over frames"},
+        "n_gpus": args.gpus, "steps": len(ts), "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": cfgd,
+        "cpu_baseline": {"value": msps, "unit": "Msamples/s", "cores": used, "kind": kind, "sample": sample},
         "e2e": {"value": msps, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -174,7 +293,88 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------ GPU arm ------
+def link_probe(torch, dist, world, h2d_bytes, d2h_bytes, reps=3):
+    """Pinned host<->device copies of one e2e step's byte mix, both directions at once, every rank at the
+    same time: the box's copy ceiling for the e2e path.  Returns aggregate GB/s over all ranks."""
+    hb = torch.empty(h2d_bytes, dtype=torch.uint8).pin_memory()
+    db = torch.empty(h2d_bytes, dtype=torch.uint8, device="cuda")
+    ho = torch.empty(d2h_bytes, dtype=torch.uint8).pin_memory()
+    do = torch.empty(d2h_bytes, dtype=torch.uint8, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    best = None
+    for i in range(reps + 1):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s1):
+            db.copy_(hb, non_blocking=True)
+        with torch.cuda.stream(s2):
+            ho.copy_(do, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        if i > 0:
+            best = dt if best is None else min(best, dt)
+    del hb, db, ho, do
+    return (h2d_bytes + d2h_bytes) * world / best / 1e9
+
+
+def run_ours_ref(args):
+    """REF workload on the GPU arm: the same kind of capture through rub_rx_process_capture (host buffer in,
+    host results out: Schmidl & Cox metric, plateau rule, timing search, LS, invert, decode of 1000 symbols)."""
+    import torch
+    import rub_mimo_b200 as rub
+    if rub.device_count() < 1:
+        raise RuntimeError("bench.py needs a CUDA device: rub_mimo_b200 has no CPU fallback")
+    g = WORKLOADS["REF"]["geom"]
+    p, Mo, cap, data, _ = ref_capture(g)
+    cfg = rub.preset("C1", M=g["M"], cp_len=g["cp"], num_access_codes=g["nac"], num_data_symbols=g["D"], sctype=p)
+    S1, s1 = rub.default_S1(cfg)
+    S0, s0 = rub.default_S0(cfg)
+    rx = rub.Receiver(cfg, S1)
+    rx.set_S0(s0)
+    txd = np.ascontiguousarray(data.transpose(1, 0, 2))[None]  # [1][N][D][Mo]
+    sampler = ClockSampler(0)
+    sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        nfound, sync, out = rx.process_capture(cap, max_frames=2, out_mask=rub.OUT_EQ | rub.OUT_RXDATA, tx_data=txd)
+    assert nfound == 1, nfound
+    l0 = rx.launch_count
+    ts = []
+    for _ in range(args.steps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        nfound, sync, out = rx.process_capture(cap, max_frames=2, out_mask=rub.OUT_EQ | rub.OUT_RXDATA, tx_data=txd)
+        ts.append(time.perf_counter() - t0)
+    launches = rx.launch_count - l0
+    sec = float(np.mean(ts))
+    n = cap.shape[1]
+    msps = 2 * n / sec / 1e6
+    ser = float(np.mean(out["rx_data"][0] != txd[0]))
+    clocks = sampler.stop()
+    line = {
+        "metric": "rx_msamples_per_s", "value": msps, "unit": "Msamples/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic (one burst in a raw capture)",
+        "config": {"workload": WORKLOADS["REF"]["label"], "capture_samples_per_stream": int(n),
+                   "note": "host capture in, host results out: value IS the end-to-end number (rub_rx_process_capture has no "
+                           "device-resident entry point)"},
+        "roofline": None, "cpu_baseline": None,
+        "e2e": {"value": msps, "unit": "Msamples/s", "h2d_bytes_per_step": int(cap.nbytes + txd.nbytes),
+                "d2h_bytes_per_step": int(out["eq"].nbytes + out["rx_data"].nbytes + 4 * n * 2), "ms_per_step": sec * 1e3},
+        "gpu_launches": int(launches), "clocks": clocks, "symbol_error_rate": ser,
+    }
+    print(json.dumps(line), flush=True)
+    rx.close()
+
+
 def run_ours(args):
+    if args.workload == "REF":
+        return run_ours_ref(args)
     import torch
     import torch.distributed as dist
     import rub_mimo_b200 as rub
@@ -216,46 +416,66 @@ def run_ours(args):
     def step():
         rx.process_batch(d_iq, out=out, out_mask=out_mask, tx_data=d_tx)
         if world > 1:
-            rx.allreduce_counters()
+            rx.allreduce_counters()   # snapshot + ncclAllReduce on a side stream: the next batch does not wait for it
 
-    for _ in range(max(args.warmup, 3)):
+    K, W = args.steps, max(args.warmup, 3)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()           # forked BEFORE the barrier, so no rank waits for it inside the timed region
+        time.sleep(0.3)
+    for _ in range(W):
         step()
     rx.sync()
     rx.reset_counters()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    # ---- timed region: rounds of exactly K steps, each bracketed by barrier + synchronize on both sides.
+    # A round of K=20 C3 steps is ~30 ms, so rounds are repeated until >= 1 s has been timed and the MEDIAN
+    # round is reported (ms_per_step); every step is also timed on its own (p50 / max expose an outlier).
+    round_ms, step_ms = [], []
     launches0 = rx.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record(rx.tstream)
-    for _ in range(args.steps):
-        step()
-    e1.record(rx.tstream)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms = e0.elapsed_time(e1)
-    launches = rx.launch_count - launches0
-    t = torch.tensor([ms], device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    counters = rx.read_counters()
+    n_rounds = 0
+    while True:
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev[0].record(rx.tstream)
+        for i in range(K):
+            step()
+            ev[i + 1].record(rx.tstream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = ev[0].elapsed_time(ev[K])
+        t = torch.tensor([ms], device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        round_ms.append(float(t.item()))
+        step_ms += [ev[i].elapsed_time(ev[i + 1]) for i in range(K)]
+        n_rounds += 1
+        stop = torch.tensor([1.0 if (sum(round_ms) >= 1000.0 or n_rounds >= 64) else 0.0], device="cuda")
+        if world > 1:
+            dist.broadcast(stop, src=0)
+        if stop.item() > 0:
+            break
+    launches = (rx.launch_count - launches0) // n_rounds
+    ms = float(np.median(round_ms))
+    local_counters = rx.read_counters()
+    counters = rx.read_counters_global() if world > 1 else local_counters
     # dominant kernel: CUDA events recorded by the library around the kernel on its stream
-    # (keep the clock sampler running so the record covers both loops)
     dom = []
-    for _ in range(args.steps):
+    for _ in range(K):
         rx.process_batch(d_iq, out=out, out_mask=out_mask, tx_data=d_tx)
         rx.sync()
         dom.append(rx.last_timing()[1])
     dom_ms = float(np.mean(dom))
     path = {rub.PATH_STAGED: "staged", rub.PATH_FUSED: "fused"}[rx.last_path]
-    step_ms = ms / args.steps
-    msps, det = metric_values(cfg, F * world, step_ms / 1e3)
+    kernel = rx.last_kernel()
+    step_ms_med = ms / K
+    Fw = F * world
+    spf = cfg.D * cfg.N * (cfg.M + cfg.cp_len)
+    msps = Fw * spf / (step_ms_med / 1e3) / 1e6
+    det = Fw * cfg.D * cfg.Mo / (step_ms_med / 1e3)
     peak, peak_src = _peaks()
     alg = rx.algorithmic_bytes(F, out_mask, True)
     if path == "staged":
@@ -265,7 +485,6 @@ def run_ours(args):
     else:
         alg_dom = alg
     achieved = alg_dom / (dom_ms / 1e3) / 1e9
-    tr = _traffic()
 
     # ---- e2e: host buffers through the C-ABI host entry point (H2D + D2H inside) ----
     e2e = None
@@ -277,7 +496,7 @@ def run_ours(args):
         h_tx = torch.from_numpy(tx_u).repeat(reps, 1, 1, 1)[:F].contiguous().pin_memory()
         h_out = rx.alloc_outputs_host(F, out_mask, pinned=True)
         cnt = np.zeros((cfg.N, 4), np.uint64)
-        e2e_steps = max(2, min(args.steps, 5))
+        e2e_steps = max(2, min(K, 5))
         for _ in range(2):
             rx.process_batch_host(h_iq.numpy(), out=h_out, out_mask=out_mask, tx_data=h_tx.numpy(), counters=cnt)
         torch.cuda.synchronize()
@@ -292,48 +511,61 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item()) / e2e_steps
-        e_msps, _ = metric_values(cfg, F * world, dt)
         h2d = h_iq.numel() * 8 + h_tx.numel()
         d2h = sum(v.nbytes for k, v in h_out.items() if not k.startswith("_")) + cnt.nbytes
-        e2e = {"value": e_msps, "unit": "Msamples/s", "h2d_bytes_per_step": int(h2d),
+        del h_iq, h_tx, h_out
+        e2e = {"value": Fw * spf / dt / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3, "steps": e2e_steps,
                "note": "rub_rx_process_batch_host, pinned host buffers (allocated on the GPU's NUMA node), "
                        "3-stream chunk pipeline"}
-        del h_iq, h_tx, h_out
+        if not args.no_probe:
+            # the box's concurrent pinned-copy ceiling for this byte mix, all ranks at once
+            link = link_probe(torch, dist, world, int(h2d), int(d2h))
+            e2e["link_peak_gbs"] = link
+            e2e["link_gbs"] = (h2d + d2h) * world / dt / 1e9
+            e2e["frac"] = e2e["link_gbs"] / link
         if old_aff:
             os.sched_setaffinity(0, old_aff)
 
-    clocks = sampler.stop() if rank == 0 else None   # covers the timed loop, the kernel loop and e2e
+    clocks = sampler.stop() if rank == 0 else None   # covers the timed rounds, the kernel loop and e2e
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from util import to_orc
         cores = os.cpu_count() or 1
-        nf = min(U, max(8, 2 * cores))
-        sec = cpu_oracle_rate(cfg, S1, iq_u[:nf], tx_u[:nf], cores)
-        sec1 = cpu_oracle_rate(cfg, S1, iq_u[:max(2, nf // 8)], tx_u[:max(2, nf // 8)], 1, reps=2)
-        c_msps, _ = metric_values(cfg, nf, sec)
-        c1_msps, _ = metric_values(cfg, max(2, nf // 8), sec1)
-        cpu = {"value": c_msps, "unit": "Msamples/s", "cores": cores, "kind": "port",
-               "sample": f"{nf} frames of the same workload, best of 3, OpenMP over frames; "
-                         f"single thread (reference decodes on one thread): {c1_msps:.3f} Msamples/s"}
+        nf = cpu_sample_frames(cores, wl["frames_per_gpu"])
+        r2 = (nf + U - 1) // U
+        iq_c, tx_c = np.tile(iq_u, (r2, 1, 1))[:nf], np.tile(tx_u, (r2, 1, 1, 1))[:nf]
+        sec, _ = cpu_port_time(to_orc(cfg), S1, iq_c, tx_c, cores, reps=3, warmup=1)
+        n1 = max(2, nf // 16)
+        sec1, _ = cpu_port_time(to_orc(cfg), S1, iq_c[:n1], tx_c[:n1], 1, reps=1, warmup=0)
+        cpu = {"value": nf * spf / sec / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "port",
+               "sample": f"{nf} frames of the same workload, mean of 3 passes after 1 warm-up, OpenMP over frames "
+                         f"(the --impl reference arm's method); single thread (the reference decodes on one thread): "
+                         f"{n1 * spf / sec1 / 1e6:.3f} Msamples/s"}
     if rank == 0:
         line = {
             "metric": "rx_msamples_per_s", "value": msps, "unit": "Msamples/s",
-            "detections_per_s": det, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "detections_per_s": det, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": step_ms_med, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": f"synthetic ({U} unique frames tiled to {F} per GPU)",
-            "config": {"workload": wl["label"], "frames_per_gpu": F, "frames_total": F * world,
-                       "outputs": args.outputs + "+counters", "path": path,
+            "config": {"workload": wl["label"], "frames_per_gpu": F, "frames_total": Fw,
+                       "outputs": args.outputs + "+counters", "path": path, "kernel": kernel,
                        "l2": "inputs+outputs per step (5.5 GB) exceed the 126 MB L2; no flush needed",
-                       "parallelism": f"frame-sharded x{world}, ncclAllReduce(uint64 counters) per step"},
+                       "parallelism": f"frame-sharded x{world}, ncclAllReduce(uint64 counters) per step on a side stream"},
+            "timing": {"rounds": n_rounds, "round_ms": [round(x, 4) for x in round_ms],
+                       "reported": "median round / steps", "step_ms_p50": float(np.median(step_ms)),
+                       "step_ms_max": float(np.max(step_ms)), "step_ms_min": float(np.min(step_ms))},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": (tr or {}).get("dram_bytes_per_launch"),
+                         "frac": achieved / peak, "traffic": _traffic(kernel, args.workload),
                          "algorithmic_bytes_per_launch": alg_dom, "kernel_ms": dom_ms,
-                         "kernel": {"fused": "k_rx_fused"}.get(path, "k_detect"), "peak_source": peak_src},
+                         "kernel": kernel, "peak_source": peak_src},
             "cpu_baseline": cpu,
             "e2e": e2e,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "ber": float(counters[:, 0].sum() / max(1, counters[:, 1].sum())),
+            "counters_consistent": bool(world == 1 or (counters[:, 1] == local_counters[:, 1] * world).all()),
         }
         print(json.dumps(line), flush=True)
     rx.close()
@@ -353,6 +585,7 @@ def main():
     ap.add_argument("--outputs", default="eq+llr+bits", help="subset of eq+llr+bits+rx_data (default: all three)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-probe", action="store_true", help="skip the pinned-copy ceiling probe of the e2e leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

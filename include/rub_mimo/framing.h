@@ -25,6 +25,7 @@
 #ifndef RUB_MIMO_FRAMING_H
 #define RUB_MIMO_FRAMING_H
 
+#include <algorithm>
 #include <complex>
 #include <cstdio>
 #include <cstring>
@@ -197,7 +198,9 @@ class framesync {
   unsigned int access_code_buffer_len, tx_sig_len;
   std::vector<unsigned long int> plateau_start, plateau_end;
   std::vector<bool> in_plateau;
-  std::vector<std::vector<gr_complex> > history;  // every sample pushed so far (windowcf stand-in)
+  // windowcf / wdelay stand-in: the most recent samples of every stream.  Only the last Wlen (estimate_channel)
+  // or M + M/2 (metric look-back) are ever read, so execute() trims it to that bound (amortised O(1))
+  std::vector<std::vector<gr_complex> > history;
   rub_rx *rx;       // decode handle (created once the number of buffered payload symbols is known)
   rub_rx *rx_sync;  // handle used for the synchronisation kernels
   std::vector<int32_t> corr_indices;  // [rx][ac_id]
@@ -328,7 +331,13 @@ class framesync {
       num_samples_processed++;
       if (break_loop) break;
     }
+    trim_history();
     return state;
+  }
+  void trim_history() {
+    const size_t keep = std::max((size_t)access_code_buffer_len + tx_sig_len, (size_t)(M + M2));
+    for (unsigned int s = 0; s < num_streams; s++)
+      if (history[s].size() > 2 * keep) history[s].erase(history[s].begin(), history[s].end() - (long)keep);
   }
 
   // framing.cc:653-886

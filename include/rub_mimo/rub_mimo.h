@@ -138,6 +138,13 @@ typedef struct rub_rx_io {
   uint8_t *bits;
   uint8_t *rx_data;
   float *G;
+  /* error counters [stream][bit errors, bits, symbol errors, symbols] (uint64), only with tx_data.
+   *   rub_rx_process_batch:       a DEVICE pointer the kernels atomicAdd this batch's counts into, or NULL to
+   *                               accumulate in the handle's own device counters (rub_rx_read_counters);
+   *   rub_rx_process_batch_host,
+   *   rub_rx_process_capture:     a HOST pointer that receives a copy of the handle's CUMULATIVE counters
+   *                               after the call (not this batch's alone; rub_rx_reset_counters zeroes them).
+   * Passing a host pointer to rub_rx_process_batch is an error the library cannot detect.                 */
   uint64_t *counters;
   uint32_t out_mask;
 } rub_rx_io;
@@ -163,6 +170,8 @@ rub_status rub_rx_process_batch(rub_rx *h, const rub_rx_io *io, uint32_t n_frame
  * chain, copies the requested outputs back, in chunks pipelined over internal streams.
  * Synchronous.  This is what the framing.h facade and the offline IQ-file driver call. */
 rub_status rub_rx_process_batch_host(rub_rx *h, const rub_rx_io *io, uint32_t n_frames);
+/* frames per pipeline chunk of rub_rx_process_batch_host (0 = automatic, about 256 MB of traffic)  */
+rub_status rub_rx_set_host_chunk(rub_rx *h, uint32_t frames);
 
 rub_status rub_rx_sync(rub_rx *h);
 rub_status rub_rx_set_path(rub_rx *h, uint32_t path);
@@ -176,6 +185,8 @@ uint64_t rub_rx_launch_count(const rub_rx *h);
 /* CUDA-event time of the last rub_rx_process_batch on the handle's stream, in ms;
  * requires rub_rx_sync first.  dominant_ms = the detect/fused kernel alone.             */
 rub_status rub_rx_last_timing(rub_rx *h, float *total_ms, float *dominant_ms);
+/* name of the dominant kernel of the last batch ("k_rx_ws", "k_rx_fused", "k_detect_lean", "k_detect") */
+const char *rub_rx_last_kernel(const rub_rx *h);
 /* algorithmic bytes of one rub_rx_process_batch call (SURVEY.md 8d formula)             */
 uint64_t rub_rx_algorithmic_bytes(const rub_rx *h, uint32_t n_frames, uint32_t out_mask,
                                   int with_tx_data);

@@ -105,8 +105,8 @@ class rub_synth_params(C.Structure):
 ABI_SYMBOLS = [
     "rub_config_num_training_symbols", "rub_config_num_occupied", "rub_config_validate",
     "rub_rx_create", "rub_rx_destroy", "rub_rx_process_batch", "rub_rx_process_batch_host",
-    "rub_rx_sync", "rub_rx_set_path", "rub_rx_get_path", "rub_rx_reset_counters",
-    "rub_rx_device_counters", "rub_rx_read_counters", "rub_rx_launch_count", "rub_rx_last_timing",
+    "rub_rx_sync", "rub_rx_set_path", "rub_rx_get_path", "rub_rx_reset_counters", "rub_rx_set_host_chunk",
+    "rub_rx_device_counters", "rub_rx_read_counters", "rub_rx_launch_count", "rub_rx_last_timing", "rub_rx_last_kernel",
     "rub_rx_algorithmic_bytes", "rub_rx_sc_metric", "rub_rx_timing_search", "rub_rx_set_S0",
     "rub_framegen_batch_device", "rub_rx_process_files", "rub_config_from_args", "rub_config_from_json", "rub_rx_process_capture",
     "rub_comm_get_unique_id", "rub_comm_init", "rub_allreduce_counters", "rub_rx_read_counters_global",
@@ -166,6 +166,7 @@ def lib():
         for f in ("rub_rx_sync", "rub_rx_reset_counters", "rub_allreduce_counters", "rub_comm_destroy"):
             getattr(L, f).argtypes = [C.c_void_p]
         L.rub_rx_set_path.argtypes = [C.c_void_p, C.c_uint32]
+        L.rub_rx_set_host_chunk.argtypes = [C.c_void_p, C.c_uint32]
         L.rub_rx_get_path.argtypes = [C.c_void_p]
         L.rub_rx_launch_count.argtypes = [C.c_void_p]
         L.rub_rx_device_counters.argtypes = [C.c_void_p]
@@ -173,6 +174,8 @@ def lib():
         L.rub_rx_read_counters_global.argtypes = [C.c_void_p, C.c_void_p]
         L.rub_rx_read_counters_global.restype = C.c_int
         L.rub_rx_last_timing.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.rub_rx_last_kernel.argtypes = [C.c_void_p]
+        L.rub_rx_last_kernel.restype = C.c_char_p
         L.rub_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.rub_rx_sc_metric.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         L.rub_rx_timing_search.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
@@ -474,6 +477,10 @@ class Receiver:
     def set_path(self, path):
         _check(lib().rub_rx_set_path(self.h, path))
 
+    def set_host_chunk(self, frames):
+        """frames per pipeline chunk of process_batch_host (0 = automatic)"""
+        _check(lib().rub_rx_set_host_chunk(self.h, frames))
+
     @property
     def last_path(self):
         return int(lib().rub_rx_get_path(self.h))
@@ -487,6 +494,9 @@ class Receiver:
 
     def reset_counters(self):
         _check(lib().rub_rx_reset_counters(self.h))
+
+    def last_kernel(self):
+        return lib().rub_rx_last_kernel(self.h).decode()
 
     def read_counters(self):
         out = np.zeros((self.cfg.N, 4), np.uint64)

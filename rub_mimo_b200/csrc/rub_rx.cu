@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <thread>
 #include <vector>
 
@@ -95,6 +96,7 @@ struct rub_rx {
   bool fused_unfit = false;  // no fused kernel fits this configuration (shared memory): staged path
   uint64_t *d_counters = nullptr;
   uint32_t path = RUB_PATH_AUTO, last_path = 0;
+  const char *last_kernel = "";
   uint64_t launches = 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   bool timed = false;
@@ -102,6 +104,7 @@ struct rub_rx {
   cudaStream_t s_in = nullptr, s_out = nullptr;
   void *d_pipe = nullptr;
   size_t pipe_bytes = 0;
+  uint32_t host_chunk = 0;  // frames per pipeline chunk of the host entry point (0 = sized to ~256 MB)
   cudaEvent_t pev[12] = {};
   // comm: the counter all-reduce runs on its own stream against double-buffered snapshots
   void *comm = nullptr;
@@ -265,8 +268,14 @@ extern "C" rub_status rub_rx_set_path(rub_rx *h, uint32_t path) {
   h->path = path;
   return RUB_OK;
 }
+extern "C" rub_status rub_rx_set_host_chunk(rub_rx *h, uint32_t frames) {
+  if (!h) return RUB_ERR_INVALID_ARG;
+  h->host_chunk = frames;
+  return RUB_OK;
+}
 extern "C" uint32_t rub_rx_get_path(const rub_rx *h) { return h ? h->last_path : 0; }
 extern "C" uint64_t rub_rx_launch_count(const rub_rx *h) { return h ? h->launches : 0; }
+extern "C" const char *rub_rx_last_kernel(const rub_rx *h) { return h ? h->last_kernel : ""; }
 extern "C" uint64_t *rub_rx_device_counters(rub_rx *h) { return h ? h->d_counters : nullptr; }
 extern "C" rub_status rub_rx_reset_counters(rub_rx *h) {
   if (!h) return RUB_ERR_INVALID_ARG;
@@ -318,13 +327,14 @@ static void launch_fft(const ChainArgs &a, cudaStream_t st, cudaError_t *err) {
   constexpr int NT = FftPlan<LOG2M>::NT;
   constexpr int F = NT >= 128 ? 1 : 128 / NT;
   const size_t smem = (size_t)F * 2 * fft_padded_size(1 << LOG2M) * sizeof(cf);
-  static bool attr_done[16] = {};
+  // the attribute is per device and per function: set once per device, safely across host threads
+  static std::atomic<bool> attr_done[64];
   int dev = 0;
   cudaGetDevice(&dev);
-  if (!attr_done[dev & 15]) {
+  if (!attr_done[dev & 63].load(std::memory_order_acquire)) {
     *err = cudaFuncSetAttribute(k_fft_staged<LOG2M, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (*err != cudaSuccess) return;
-    attr_done[dev & 15] = true;
+    attr_done[dev & 63].store(true, std::memory_order_release);
   }
   const long long total = (long long)a.n_frames * (a.T + a.D) * a.N;
   const unsigned grid = (unsigned)((total + F - 1) / F);
@@ -337,8 +347,10 @@ static void launch_weights_detect(const ChainArgs &a, const rub_rx *h, cudaStrea
   if (e0) cudaEventRecord(e0, st);
   if (detect_lean_launch(a, h->lut, st)) {
     if (e1) cudaEventRecord(e1, st);
+    const_cast<rub_rx *>(h)->last_kernel = "k_detect_lean";
     return;
   }
+  const_cast<rub_rx *>(h)->last_kernel = "k_detect";
   const int groups = (a.Mo + 7) / 8;
   dim3 grid((unsigned)((long long)a.n_frames * a.D * N), (unsigned)((groups + 127) / 128));
   k_detect<N><<<grid, 128, 0, st>>>(a, h->lut);
@@ -459,6 +471,7 @@ static rub_status run_fused(rub_rx *h, const ChainArgs &a, uint32_t n_frames, bo
   h->launches += 1;
   CUDA_TRY(cudaGetLastError());
   h->last_path = RUB_PATH_FUSED;
+  h->last_kernel = h->ws ? "k_rx_ws" : "k_rx_fused";
   return RUB_OK;
 }
 
@@ -517,9 +530,6 @@ extern "C" rub_status rub_rx_process_batch(rub_rx *h, const rub_rx_io *io, uint3
 // chunked 3-stream pipeline: H2D (s_in) -> chain (handle stream) -> D2H (s_out), two slots
 extern "C" rub_status rub_rx_process_batch_host(rub_rx *h, const rub_rx_io *io, uint32_t n_frames) {
   if (!h || !io || !io->iq) { set_error("process_batch_host: NULL argument"); return RUB_ERR_INVALID_ARG; }
-  if (io->timing || io->payload_start) {
-    // timing tables are small: run un-pipelined through a temporary device copy
-  }
   const HostCfg &c = h->h;
   CUDA_TRY(cudaSetDevice(h->device));
   if (!h->s_in) {
@@ -543,6 +553,7 @@ extern "C" rub_status rub_rx_process_batch_host(rub_rx *h, const rub_rx_io *io, 
   const size_t per_frame = in_b + eq_b + llr_b + bits_b + rxd_b + g_b + tx_b + tim_b + ps_b;
   // chunk sized to ~256 MB of traffic so copies and compute overlap
   uint32_t chunk = (uint32_t)std::max<size_t>(1, std::min<size_t>(n_frames, ((size_t)256 << 20) / std::max<size_t>(1, per_frame)));
+  if (h->host_chunk) chunk = std::min<uint32_t>(h->host_chunk, std::max<uint32_t>(1, n_frames));
   const size_t slot_b = al(in_b * chunk) + al(eq_b * chunk) + al(llr_b * chunk) + al(bits_b * chunk) +
                         al(rxd_b * chunk) + al(g_b * chunk) + al(tx_b * chunk) + al(tim_b * chunk) + al(ps_b * chunk) + 4096;
   if (2 * slot_b > h->pipe_bytes) {

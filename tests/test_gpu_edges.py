@@ -154,3 +154,39 @@ def test_handle_lifecycle_does_not_leak_device_memory():
     torch.cuda.empty_cache()
     free1, _ = torch.cuda.mem_get_info()
     assert free0 - free1 < (8 << 20), f"leaked {(free0 - free1) >> 20} MiB over 30 handle lifecycles"
+
+
+@pytest.mark.parametrize("chunk", [1, 2, 3])
+def test_host_pipeline_with_many_chunks(chunk):
+    """rub_rx_process_batch_host with 3+ pipeline chunks (slot reuse: the waits on the previous compute /
+    copy-out of a slot) returns what the oracle computes, and the host counters are the cumulative ones."""
+    cfg, S1, iq, tx = make_case(small_cfg(), 7, seed=21, n_taps=2, snr_db=14.0)
+    ref = oracle_run(cfg, S1, iq, tx)
+    rx = rub.Receiver(cfg, S1)
+    rx.set_host_chunk(chunk)
+    cnt = np.zeros((cfg.N, 4), np.uint64)
+    out = rx.process_batch_host(iq, out_mask=MASK, tx_data=tx, counters=cnt)
+    got = {k: v for k, v in out.items() if not k.startswith("_")}
+    got["counters"] = cnt
+    assert_parity(ref, got, cfg.q)
+    rx.process_batch_host(iq, out_mask=MASK, tx_data=tx, counters=cnt)     # cumulative on the second call
+    assert np.array_equal(cnt, 2 * ref["counters"])
+    rx.close()
+
+
+def test_allreduce_is_idempotent_on_one_rank():
+    """rub_allreduce_counters never modifies the local counters: after any number of calls the global
+    counters of a single-rank job equal the local cumulative ones (the in-place reduction
+    compounded them)."""
+    import torch
+    cfg, S1, iq, tx = make_case(small_cfg(), 3, seed=9, n_taps=2, snr_db=10.0)
+    ref = oracle_run(cfg, S1, iq, tx)["counters"]
+    rx = rub.Receiver(cfg, S1)
+    d_iq, d_tx = torch.from_numpy(iq).cuda(), torch.from_numpy(tx).cuda()
+    for step in range(1, 5):
+        rx.process_batch(d_iq, out_mask=rub.OUT_RXDATA, tx_data=d_tx)
+        rx.allreduce_counters()
+        rx.allreduce_counters()
+        assert np.array_equal(rx.read_counters_global(), step * ref)
+        assert np.array_equal(rx.read_counters(), step * ref)
+    rx.close()

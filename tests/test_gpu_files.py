@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import rub_mimo_b200 as rub
-from util import make_case
+from util import make_case, oracle_run
 
 pytestmark = pytest.mark.gpu
 
@@ -58,6 +58,14 @@ def test_file_driver_matches_batch_call(tmp_path, chunk):
     assert np.array_equal(np.fromfile(tmp_path / "llr.dat", np.float32), out["llr"].cpu().numpy().reshape(-1))
     assert np.array_equal(np.fromfile(tmp_path / "bits.dat", np.uint8), out["bits"].cpu().numpy().reshape(-1))
     assert np.array_equal(c_files, ref_rx.read_counters())
+    # ... and the files hold what the CPU oracle computes from the same frames
+    ref = oracle_run(cfg, S1, iq, tx)
+    for s in range(cfg.N):
+        assert np.array_equal(np.fromfile(eq_paths[s], np.complex64), ref["eq"][:, s].reshape(-1))
+        assert np.array_equal(np.fromfile(rd_paths[s], np.uint32), ref["rx_data"][:, s].reshape(-1).astype(np.uint32))
+    assert np.array_equal(np.fromfile(tmp_path / "llr.dat", np.float32), ref["llr"].reshape(-1))
+    assert np.array_equal(np.fromfile(tmp_path / "bits.dat", np.uint8), ref["bits"].reshape(-1))
+    assert np.array_equal(c_files, ref["counters"])
 
 
 def test_short_capture_stops_at_last_complete_frame(tmp_path):
