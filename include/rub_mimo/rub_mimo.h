@@ -198,6 +198,22 @@ uint64_t rub_rx_algorithmic_bytes(const rub_rx *h, uint32_t n_frames, uint32_t o
  * GPU thread per output sample evaluates both sums oldest-to-newest, which is the summation
  * order of the oracle: the metric is bit-exact.  x and y are HOST buffers.                  */
 rub_status rub_rx_sc_metric(rub_rx *h, const float *x, uint64_t num_samples, float *y);
+/* The same metric in a selectable form.  RUB_SYNC_FIR: as above (the reference's two FIR dot products per
+ * sample in liquid's order: O(M) per sample, bit-identical metric, so y crosses PLATEAU_THREASHOLD exactly
+ * where the reference's does).  RUB_SYNC_SCAN: sliding sums P(n) = P(n-1) + c(n) - c(n-M/2), R likewise, one
+ * block scan per tile of 2048 samples: O(1) per sample; the sums are added in another order, so y differs in
+ * the last bits and a plateau start can move by a sample where y sits within rounding of the threshold.      */
+#define RUB_SYNC_FIR 0u
+#define RUB_SYNC_SCAN 1u
+rub_status rub_rx_sc_metric_ex(rub_rx *h, const float *x, uint64_t num_samples, float *y, uint32_t mode);
+/* metric form used by rub_rx_process_capture (default RUB_SYNC_SCAN)                                          */
+rub_status rub_rx_set_sync_mode(rub_rx *h, uint32_t mode);
+/* Debug sinks of the reference's DEBUG_LOG build (mimo/framing.cc:598-600, :676-680, :873-883; read by
+ * mimo/apps/plot.py:27-40): when dir is set, rub_rx_process_capture writes dir/f_sc_<s>.dat (float32 metric of
+ * every capture sample of rx stream s = 1..N) and, for the last burst found, dir/corr_<s>_<a>.dat (float32
+ * [access_code_buffer_len - M] correlation powers |X . conj(S1)|^2 / M^2 at the candidate offsets of access code
+ * a = 1..nac*N; a = 0 = the S0 preamble, only after rub_rx_set_S0).  NULL or "" switches them off.            */
+rub_status rub_rx_set_debug_dir(rub_rx *h, const char *dir);
 /* Access-code timing search of estimate_channel (mimo/framing.cc:702-744, USE_NEW_CHANNEL_EST)
  * over the window buffer (HOST, [N][window_len] complex64, oldest sample first): for every
  * candidate i in [0, M+cp) and every (rx, ac_id) it correlates the M samples at

@@ -27,6 +27,7 @@ EST_LS_FULLBAND, EST_LS_COMB_INTERP = 0, 1
 FLAG_Q1_IDENTITY_INIT, FLAG_MMSE_UNBIASED, FLAG_ZF_CHOLESKY = 1, 2, 4
 OUT_EQ, OUT_LLR, OUT_BITS, OUT_RXDATA, OUT_G = 1, 2, 4, 8, 16
 PATH_AUTO, PATH_STAGED, PATH_FUSED = 0, 1, 2
+SYNC_FIR, SYNC_SCAN = 0, 1
 NCCL_UNIQUE_ID_BYTES = 128
 
 
@@ -105,7 +106,7 @@ class rub_synth_params(C.Structure):
 ABI_SYMBOLS = [
     "rub_config_num_training_symbols", "rub_config_num_occupied", "rub_config_validate",
     "rub_rx_create", "rub_rx_destroy", "rub_rx_process_batch", "rub_rx_process_batch_host",
-    "rub_rx_sync", "rub_rx_set_path", "rub_rx_get_path", "rub_rx_reset_counters", "rub_rx_set_host_chunk",
+    "rub_rx_sc_metric_ex", "rub_rx_set_sync_mode", "rub_rx_set_debug_dir", "rub_rx_sync", "rub_rx_set_path", "rub_rx_get_path", "rub_rx_reset_counters", "rub_rx_set_host_chunk",
     "rub_rx_device_counters", "rub_rx_read_counters", "rub_rx_launch_count", "rub_rx_last_timing", "rub_rx_last_kernel",
     "rub_rx_algorithmic_bytes", "rub_rx_sc_metric", "rub_rx_timing_search", "rub_rx_set_S0",
     "rub_framegen_batch_device", "rub_rx_process_files", "rub_config_from_args", "rub_config_from_json", "rub_rx_process_capture",
@@ -178,6 +179,9 @@ def lib():
         L.rub_rx_last_kernel.restype = C.c_char_p
         L.rub_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.rub_rx_sc_metric.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        L.rub_rx_sc_metric_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32]
+        L.rub_rx_set_sync_mode.argtypes = [C.c_void_p, C.c_uint32]
+        L.rub_rx_set_debug_dir.argtypes = [C.c_void_p, C.c_char_p]
         L.rub_rx_timing_search.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
         L.rub_framegen_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64,
                                                 C.c_uint64, C.c_float]
@@ -665,12 +669,20 @@ class Receiver:
         return out
 
     # -- synchronisation rows (f1/f2) --
-    def sc_metric(self, x):
-        """Schmidl & Cox metric of one stream (framing.cc:626-637); x numpy complex64."""
+    def sc_metric(self, x, mode=SYNC_FIR):
+        """Schmidl & Cox metric of one stream (framing.cc:626-637); x numpy complex64.  mode SYNC_FIR is the
+        reference's bit-exact FIR form, SYNC_SCAN the O(1)-per-sample sliding sums."""
         x = np.ascontiguousarray(x, np.complex64)
         y = np.empty(x.size, np.float32)
-        _check(lib().rub_rx_sc_metric(self.h, _p(x), x.size, _p(y)))
+        _check(lib().rub_rx_sc_metric_ex(self.h, _p(x), x.size, _p(y), mode))
         return y
+
+    def set_sync_mode(self, mode):
+        _check(lib().rub_rx_set_sync_mode(self.h, mode))
+
+    def set_debug_dir(self, path):
+        """f_sc_%d.dat / corr_%d_%d.dat sinks of process_capture (None = off)"""
+        _check(lib().rub_rx_set_debug_dir(self.h, None if path is None else str(path).encode()))
 
     def set_S0(self, s0):
         s0 = np.ascontiguousarray(s0, np.complex64)

@@ -59,7 +59,8 @@ __global__ void __launch_bounds__(256) k_sc_metric(const cf *__restrict__ x, uns
 __global__ void __launch_bounds__(256) k_timing_search(const cf *__restrict__ window, unsigned long long wlen,
                                                        unsigned long long rx_stride, const long long *__restrict__ win_off,
                                                        const cf *__restrict__ s1, const cf *__restrict__ s0, int M,
-                                                       int L, int N, int nac, unsigned long long *__restrict__ keys) {
+                                                       int L, int N, int nac, unsigned long long *__restrict__ keys,
+                                                       float *__restrict__ corr_out, float corr_scale_s0) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   cf *tpl = reinterpret_cast<cf *>(sm_raw);  // [M]
   cf *xs = tpl + M;                          // [M + 256]
@@ -91,10 +92,213 @@ __global__ void __launch_bounds__(256) k_timing_search(const cf *__restrict__ wi
     ay = fmaf(xv.y, tv.x, ay); ay = fmaf(-xv.x, tv.y, ay);
   }
   const float v = ax * ax + ay * ay;
+  // debug sink (corr_%d_%d.dat, framing.cc:873-883): the reference stores |X . conj(S)|^2 / M^2.  The time-domain
+  // templates are IFFT(S) * g with g = 1/sqrt(M) for the access codes and 1/sqrt(M_S0) for S0, so that is
+  // v / (g^2 M^2) = v / M, or v * M_S0 / M^2 for S0 (corr_scale_s0)
+  if (corr_out) corr_out[((size_t)blockIdx.z * gridDim.y + blockIdx.y) * L + i] = slot == 0 ? v * corr_scale_s0 : v / (float)M;
   if (v > 0.f) {
     const unsigned long long key = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);
     atomicMax(keys + (size_t)blockIdx.z * gridDim.y + blockIdx.y, key);
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Schmidl & Cox metric as sliding sums (row f2 of SURVEY.md 8): P(n) = P(n-1) + c(n) - c(n - M/2),
+// R(n) = R(n-1) + e(n) - e(n - M), c(u) = -conj(x[u - M/2]) x[u], e(u) = 0.5 |x[u]|^2.  A CTA owns a tile of
+// 256 * PER outputs of one stream (blockIdx.y): it sums the windows ending just before the tile directly
+// (block reduction), then scans the per-sample differences (thread-local prefix + block scan), so the work is
+// O(1) per sample and the rounding error cannot grow beyond a tile.  The sums are added in another order than
+// liquid's firfilt dot products, so y differs from k_sc_metric in the last bits: the plateau start can move
+// where y sits within rounding of the threshold.  k_sc_metric is the form that reproduces the reference's
+// threshold crossings bit for bit; this one is the fast path of rub_rx_process_capture.
+template <int PER>
+__global__ void __launch_bounds__(256) k_sc_metric_scan(const cf *__restrict__ x, unsigned long long n_total,
+                                                        unsigned long long row_stride, int M, float *__restrict__ y) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  cf *xs = reinterpret_cast<cf *>(sm_raw);
+  __shared__ float red[3][8];
+  __shared__ float base[3];
+  constexpr int TILE = 256 * PER;
+  const int M2 = M / 2, halo = M + M2, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const long long n0 = (long long)blockIdx.x * TILE;
+  x += (size_t)blockIdx.y * row_stride;
+  y += (size_t)blockIdx.y * row_stride;
+  for (int i = tid; i < halo + TILE; i += 256) {
+    const long long g = n0 - halo + i;
+    xs[i] = (g >= 0 && g < (long long)n_total) ? x[g] : mk(0.f, 0.f);
+  }
+  __syncthreads();
+  auto cterm = [&](int i) {  // c(u) for the sample at xs[i]
+    const cf xv = xs[i], d = xs[i - M2];
+    return mk(-(d.x * xv.x + d.y * xv.y), -(d.x * xv.y - d.y * xv.x));
+  };
+  auto eterm = [&](int i) { const cf xv = xs[i]; return 0.5f * (xv.x * xv.x + xv.y * xv.y); };
+  // windows ending at n0 - 1: xs[halo - M2 .. halo) for P, xs[halo - M .. halo) for R
+  float px = 0.f, py = 0.f, r = 0.f;
+  for (int i = halo - M2 + tid; i < halo; i += 256) { const cf c = cterm(i); px += c.x; py += c.y; }
+  for (int i = halo - M + tid; i < halo; i += 256) r += eterm(i);
+  auto block_sum3 = [&](float &a, float &b, float &c) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    if (lane == 0) { red[0][wid] = a; red[1][wid] = b; red[2][wid] = c; }
+    __syncthreads();
+    if (tid < 3) { float t = 0.f; for (int w = 0; w < 8; w++) t += red[tid][w]; base[tid] = t; }
+    __syncthreads();
+  };
+  block_sum3(px, py, r);
+  const float bpx = base[0], bpy = base[1], br = base[2];
+  __syncthreads();
+  // per-thread inclusive prefix of the differences of its PER consecutive outputs
+  float dpx[PER], dpy[PER], dr[PER];
+  float tx = 0.f, ty = 0.f, tr = 0.f;
+#pragma unroll
+  for (int k = 0; k < PER; k++) {
+    const int i = halo + tid * PER + k;
+    const cf cn = cterm(i), co = cterm(i - M2);
+    tx += cn.x - co.x; ty += cn.y - co.y; tr += eterm(i) - eterm(i - M);
+    dpx[k] = tx; dpy[k] = ty; dr[k] = tr;
+  }
+  // exclusive block scan of the thread totals
+  float sx = tx, sy = ty, sr = tr;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float ax = __shfl_up_sync(0xffffffffu, sx, o), ay = __shfl_up_sync(0xffffffffu, sy, o), ar = __shfl_up_sync(0xffffffffu, sr, o);
+    if (lane >= o) { sx += ax; sy += ay; sr += ar; }
+  }
+  if (lane == 31) { red[0][wid] = sx; red[1][wid] = sy; red[2][wid] = sr; }
+  __syncthreads();
+  float ox = sx - tx, oy = sy - ty, orr = sr - tr;  // exclusive within the warp
+  for (int w = 0; w < wid; w++) { ox += red[0][w]; oy += red[1][w]; orr += red[2][w]; }
+#pragma unroll
+  for (int k = 0; k < PER; k++) {
+    const long long n = n0 + tid * PER + k;
+    if (n < (long long)n_total) {
+      const float Px = bpx + (ox + dpx[k]), Py = bpy + (oy + dpy[k]), R = br + (orr + dr[k]);
+      y[n] = (Px * Px + Py * Py) / (R * R);
+    }
+  }
+}
+
+// ok[n] = 1 when y[n - cp - 1 .. n] are all above the threshold, i.e. the reference's plateau rule
+// (framing.cc:601-616: in_plateau && plateau_end - plateau_start > cp_len) holds for this stream at sample n.
+// Tile + look-back of cp + 1 samples per CTA; "index of the last sample at or below the threshold" is a block
+// max-scan.  Samples before the capture count as below.
+__global__ void __launch_bounds__(256) k_plateau_ok(const float *__restrict__ y, unsigned long long n_total,
+                                                    unsigned long long row_stride, int cp, float threshold,
+                                                    unsigned char *__restrict__ ok) {
+  __shared__ long long wmax[8];
+  constexpr int TILE = 1024;
+  const int halo = cp + 1, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const long long n0 = (long long)blockIdx.x * TILE, first = n0 - halo;
+  y += (size_t)blockIdx.y * row_stride;
+  ok += (size_t)blockIdx.y * row_stride;
+  const int total = halo + TILE, per = (total + 255) / 256;
+  // thread-local last-below index over its contiguous chunk
+  const int c0 = tid * per, c1 = min(total, c0 + per);
+  long long last = first - 1;  // "the sample before the region is below": harmless, the region reaches cp + 1 back
+  for (int i = c0; i < c1; i++) {
+    const long long g = first + i;
+    const bool above = g >= 0 && g < (long long)n_total && y[g] > threshold;
+    if (!above) last = g;
+  }
+  // inclusive block max-scan of the chunk results
+  long long s = last;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const long long a = __shfl_up_sync(0xffffffffu, s, o);
+    if (lane >= o && a > s) s = a;
+  }
+  if (lane == 31) wmax[wid] = s;
+  __syncthreads();
+  long long before = __shfl_up_sync(0xffffffffu, s, 1);  // exclusive within the warp
+  if (lane == 0) before = first - 1;
+  for (int w = 0; w < wid; w++) before = max(before, wmax[w]);
+  long long run = before;
+  for (int i = c0; i < c1; i++) {
+    const long long g = first + i;
+    const bool above = g >= 0 && g < (long long)n_total && y[g] > threshold;
+    if (!above) run = g;
+    if (i >= halo && g < (long long)n_total) ok[g] = (g - run >= (long long)cp + 2) ? 1 : 0;
+  }
+}
+
+// The receive loop's state machine over a whole capture (framing.cc:591-651), one CTA: find the first sample
+// at which every stream's plateau rule holds, take the streams' plateau starts (walking back over the metric),
+// sync_index = their mean, skip the access codes and the payload, and search again behind the burst.
+struct PlateauWalk {
+  long long n, L, acb_len, tx_sig_len, Wlen;
+  int N, cp;
+  float threshold;
+  unsigned max_frames;
+};
+__global__ void __launch_bounds__(1024) k_plateau_walk(const unsigned char *__restrict__ ok, const float *__restrict__ y,
+                                                       unsigned long long row_stride, PlateauWalk w,
+                                                       long long *__restrict__ win_off, unsigned long long *__restrict__ syncs,
+                                                       unsigned *__restrict__ count) {
+  __shared__ long long s_found, s_pos, s_pstart[8];
+  __shared__ int s_done;
+  const int tid = threadIdx.x;
+  if (tid == 0) { s_pos = 0; s_done = 0; *count = 0; }
+  __syncthreads();
+  unsigned cnt = 0;
+  while (cnt < w.max_frames) {
+    const long long pos = s_pos;
+    long long found = -1;
+    for (long long b0 = pos + w.cp + 1; b0 < w.n; b0 += 1024 * 8) {
+      if (tid == 0) s_found = 0x7fffffffffffffffLL;
+      __syncthreads();
+      long long best = 0x7fffffffffffffffLL;
+      for (int k = 0; k < 8; k++) {
+        const long long i = b0 + tid + (long long)k * 1024;
+        if (i >= w.n) break;
+        bool all = true;
+        for (int s = 0; s < w.N; s++) all = all && ok[(size_t)s * row_stride + i];
+        if (all) { best = i; break; }
+      }
+      for (int o = 16; o; o >>= 1) { const long long t = __shfl_xor_sync(0xffffffffu, best, o); if (t < best) best = t; }
+      if ((tid & 31) == 0 && best != 0x7fffffffffffffffLL) atomicMin((unsigned long long *)&s_found, (unsigned long long)best);
+      __syncthreads();
+      if (s_found != 0x7fffffffffffffffLL) { found = s_found; break; }
+      __syncthreads();
+    }
+    if (found < 0) break;
+    // plateau start of every stream: the run of above-threshold samples that contains found, clipped at pos
+    if (tid < w.N) {
+      long long g = found - w.cp - 1;
+      const float *ys = y + (size_t)tid * row_stride;
+      while (g - 1 >= pos && ys[g - 1] > w.threshold) g--;
+      s_pstart[tid] = g;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long si = 0;
+      for (int s = 0; s < w.N; s++) si += (unsigned long long)s_pstart[s];
+      si /= (unsigned)w.N;
+      const long long i_switch = (long long)si + w.tx_sig_len + w.acb_len - w.L;  // first sample that is not buffered
+      if (i_switch > w.n || i_switch < w.Wlen) s_done = 1;                        // the burst runs past the capture
+      else { win_off[cnt] = i_switch - w.Wlen; syncs[cnt] = si; *count = cnt + 1; s_pos = i_switch + 1; }
+    }
+    __syncthreads();
+    if (s_done) break;
+    cnt++;
+  }
+}
+
+// keys of the batched timing search -> per-link FFT window starts (quirk Q2) and the payload start taken from
+// rx stream 1's last access code (quirk Q4, framing.cc:857), in capture coordinates
+__global__ void k_timing_tables(const unsigned long long *__restrict__ keys, const long long *__restrict__ win_off, int F,
+                                int N, int max_ac, int L, int M, int *__restrict__ timing, int *__restrict__ pay) {
+  const int slots = max_ac + 1;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= F * N * max_ac) return;
+  const int ac = idx % max_ac, r = (idx / max_ac) % N, f = idx / (max_ac * N);
+  const unsigned long long k = keys[((size_t)f * N + r) * slots + ac + 1];
+  const unsigned off = (k >> 32) ? (unsigned)(L * (ac + 1)) + (0xffffffffu - (unsigned)(k & 0xffffffffu)) : 0u;
+  const int t = (int)(win_off[f] + off);
+  timing[((size_t)f * N + r) * max_ac + ac] = t;
+  if (r == (N > 1 ? 1 : 0) && ac == max_ac - 1) pay[f] = t + M;
 }
 
 }  // namespace rub

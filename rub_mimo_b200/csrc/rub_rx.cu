@@ -5,6 +5,7 @@
 #include <dlfcn.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string>
 #include <string.h>
 
 #include <algorithm>
@@ -75,8 +76,13 @@ struct rub_rx {
   float *d_sgn = nullptr;
   cf *d_s1 = nullptr;  // time-domain access codes [tx][code][n] (timing search)
   cf *d_s0 = nullptr;  // time-domain S0 (optional)
+  float s0_corr_scale = 0.f;  // M_S0 / M^2: turns the time-domain S0 correlation power into the reference's |X . conj(S0)|^2 / M^2
   void *d_sync = nullptr;  // grow-only scratch of the synchronisation calls
   size_t sync_bytes = 0;
+  void *d_capt = nullptr;  // grow-only scratch of rub_rx_process_capture (capture, metric, flags, outputs)
+  size_t capt_bytes = 0;
+  uint32_t sync_mode = RUB_SYNC_SCAN;  // metric form of rub_rx_process_capture
+  std::string debug_dir;               // f_sc_%d.dat / corr_%d_%d.dat sinks of rub_rx_process_capture ("" = off)
   unsigned char *d_null = nullptr;
   DemapConst lut;
   WeightMode wm;
@@ -250,7 +256,7 @@ extern "C" void rub_rx_destroy(rub_rx *h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->s_comm) cudaStreamSynchronize(h->s_comm);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
-  cudaFree(h->d_tw); cudaFree(h->d_occ); cudaFree(h->d_sgn); cudaFree(h->d_null); cudaFree(h->d_s1); cudaFree(h->d_s0); cudaFree(h->d_sync);
+  cudaFree(h->d_tw); cudaFree(h->d_occ); cudaFree(h->d_sgn); cudaFree(h->d_null); cudaFree(h->d_s1); cudaFree(h->d_s0); cudaFree(h->d_sync); cudaFree(h->d_capt);
   cudaFree(h->d_scratch); cudaFree(h->d_fW); cudaFree(h->d_fG); cudaFree(h->d_fAcc); cudaFree(h->d_sgn8); cudaFree(h->d_counters); cudaFree(h->d_pipe);
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);
   for (auto &e : h->pev) if (e) cudaEventDestroy(e);
@@ -713,12 +719,49 @@ extern "C" rub_status rub_rx_set_S0(rub_rx *h, const float *s0) {
   CUDA_TRY(cudaSetDevice(h->device));
   if (!h->d_s0) CUDA_TRY(cudaMalloc(&h->d_s0, sizeof(cf) * h->h.M));
   CUDA_TRY(cudaMemcpy(h->d_s0, s0, sizeof(cf) * h->h.M, cudaMemcpyHostToDevice));
+  {
+    // number of carriers S0 occupies (every other enabled one, framing.cc:1075-1110): the bins of FFT(s0) that are not empty
+    const HostCfg &c = h->h;
+    std::vector<cf> master, packed, X(c.M);
+    build_twiddles(c.log2M, master, packed);
+    host_fft_forward(c.log2M, reinterpret_cast<const cf *>(s0), X.data(), packed.data());
+    float mx = 0.f;
+    for (uint32_t k = 0; k < c.M; k++) mx = std::max(mx, X[k].x * X[k].x + X[k].y * X[k].y);
+    uint32_t m_s0 = 0;
+    for (uint32_t k = 0; k < c.M; k++) m_s0 += (X[k].x * X[k].x + X[k].y * X[k].y) > 0.25f * mx;
+    h->s0_corr_scale = (float)m_s0 / ((float)c.M * (float)c.M);
+  }
   return RUB_OK;
 }
 
-// framesync::execute_sc_sync(x, stream), mimo/framing.cc:626-637
-extern "C" rub_status rub_rx_sc_metric(rub_rx *h, const float *x, uint64_t n, float *y) {
+// Schmidl & Cox metric of n samples of one stream already on the device (row stride for batched streams)
+static cudaError_t launch_sc_metric(rub_rx *h, uint32_t mode, const cf *dx, uint64_t n, uint64_t row_stride, uint32_t streams, float *dy) {
+  const int M = (int)h->h.M;
+  if (mode == RUB_SYNC_SCAN) {
+    constexpr int PER = 8, TILE = 256 * PER;
+    const size_t smem = (size_t)(M + M / 2 + TILE) * sizeof(cf);
+    cudaError_t e = cudaFuncSetAttribute(k_sc_metric_scan<PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid((unsigned)((n + TILE - 1) / TILE), streams);
+    k_sc_metric_scan<PER><<<grid, 256, smem, h->stream>>>(dx, n, row_stride, M, dy);
+    h->launches += 1;
+  } else {
+    const size_t smem = (size_t)(M + M / 2 + 256) * sizeof(cf);
+    cudaError_t e = cudaFuncSetAttribute(k_sc_metric, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    for (uint32_t s = 0; s < streams; s++)
+      k_sc_metric<<<(unsigned)((n + 255) / 256), 256, smem, h->stream>>>(dx + (size_t)s * row_stride, n, M, dy + (size_t)s * row_stride);
+    h->launches += streams;
+  }
+  return cudaGetLastError();
+}
+
+// framesync::execute_sc_sync(x, stream), mimo/framing.cc:626-637.  mode RUB_SYNC_FIR: the reference's two FIR dot
+// products per sample in liquid's order (bit-identical metric, O(M) per sample); RUB_SYNC_SCAN: sliding sums
+// (O(1) per sample; last-bit differences)
+extern "C" rub_status rub_rx_sc_metric_ex(rub_rx *h, const float *x, uint64_t n, float *y, uint32_t mode) {
   if (!h || !x || !y) { set_error("sc_metric: NULL argument"); return RUB_ERR_INVALID_ARG; }
+  if (mode > RUB_SYNC_SCAN) { set_error("sc_metric: unknown mode"); return RUB_ERR_INVALID_ARG; }
   if (n == 0) return RUB_OK;
   CUDA_TRY(cudaSetDevice(h->device));
   void *scr = nullptr;
@@ -727,19 +770,25 @@ extern "C" rub_status rub_rx_sc_metric(rub_rx *h, const float *x, uint64_t n, fl
   if (st) return st;
   cf *dx = reinterpret_cast<cf *>(scr);
   float *dy = reinterpret_cast<float *>((unsigned char *)scr + xb);
-  const int M = (int)h->h.M;
-  const size_t smem = (size_t)(M + M / 2 + 256) * sizeof(cf);
-  cudaError_t e = cudaFuncSetAttribute(k_sc_metric, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(dx, x, sizeof(cf) * n, cudaMemcpyHostToDevice, h->stream);
-  if (e == cudaSuccess) {
-    k_sc_metric<<<(unsigned)((n + 255) / 256), 256, smem, h->stream>>>(dx, n, M, dy);
-    h->launches += 1;
-    e = cudaGetLastError();
-  }
+  cudaError_t e = cudaMemcpyAsync(dx, x, sizeof(cf) * n, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = launch_sc_metric(h, mode, dx, n, n, 1, dy);
   if (e == cudaSuccess) e = cudaMemcpyAsync(y, dy, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
   if (e != cudaSuccess) { set_error("sc_metric: %s", cudaGetErrorString(e)); st = RUB_ERR_CUDA; }
   return st;
+}
+extern "C" rub_status rub_rx_sc_metric(rub_rx *h, const float *x, uint64_t n, float *y) {
+  return rub_rx_sc_metric_ex(h, x, n, y, RUB_SYNC_FIR);
+}
+extern "C" rub_status rub_rx_set_sync_mode(rub_rx *h, uint32_t mode) {
+  if (!h || mode > RUB_SYNC_SCAN) return RUB_ERR_INVALID_ARG;
+  h->sync_mode = mode;
+  return RUB_OK;
+}
+extern "C" rub_status rub_rx_set_debug_dir(rub_rx *h, const char *dir) {
+  if (!h) return RUB_ERR_INVALID_ARG;
+  h->debug_dir = dir ? dir : "";
+  return RUB_OK;
 }
 
 // timing search of estimate_channel, mimo/framing.cc:702-744
@@ -767,7 +816,7 @@ extern "C" rub_status rub_rx_timing_search(rub_rx *h, const float *window, uint6
   if (e == cudaSuccess) {
     dim3 grid((c.L + 255) / 256, nkeys);
     k_timing_search<<<grid, 256, smem, h->stream>>>(dw, wlen, wlen, nullptr, h->d_s1, s0_corr_index ? h->d_s0 : nullptr, (int)c.M,
-                                                    (int)c.L, (int)c.N, (int)c.nac, dk);
+                                                    (int)c.L, (int)c.N, (int)c.nac, dk, nullptr, 0.f);
     h->launches += 1;
     e = cudaGetLastError();
   }
@@ -787,10 +836,23 @@ extern "C" rub_status rub_rx_timing_search(rub_rx *h, const float *window, uint6
 }
 
 // ---------------------------------------------------------------- multi-frame capture -
-// The reference's receive loop (framesync::execute, mimo/framing.cc:471-506, :591-651, :653-886)
-// over a capture that holds any number of bursts: Schmidl & Cox metric on the GPU, the reference's
-// plateau rule walked over it on the host, one batched timing search for all bursts found, and one
-// batched LS / invert / decode call whose per-link timing tables address the capture in place.
+// The reference's receive loop (framesync::execute, mimo/framing.cc:471-506, :591-651, :653-886) over a
+// capture that holds any number of bursts, device resident from the H2D copy of the capture to the D2H copy
+// of the results: Schmidl & Cox metric (sliding sums or the bit-exact FIR form), the plateau rule per
+// stream, the state machine restarted behind every burst, one batched timing search for all bursts, the
+// per-link timing tables, and one batched LS / invert / decode launch sequence that addresses the capture rows
+// in place.  The capture sits behind a lead-in of Wlen zero samples, the content of the reference's window
+// buffer before the first sample, so a burst near the start of the capture is decoded like any other.  All
+// device scratch is cached on the handle (grow only); the host waits once for the burst count and once for
+// the results.
+static rub_status write_floats(const std::string &path, const float *p, size_t n) {
+  FILE *f = fopen(path.c_str(), "wb");
+  if (!f) { set_error("cannot open %s", path.c_str()); return RUB_ERR_IO; }
+  const bool ok = fwrite(p, sizeof(float), n, f) == n;
+  fclose(f);
+  if (!ok) { set_error("short write to %s", path.c_str()); return RUB_ERR_IO; }
+  return RUB_OK;
+}
 extern "C" rub_status rub_rx_process_capture(rub_rx *h, const float *capture, uint64_t n_samples, float threshold,
                                              uint32_t max_frames, const rub_rx_io *out, uint32_t *n_found,
                                              uint64_t *sync_index) {
@@ -800,131 +862,141 @@ extern "C" rub_status rub_rx_process_capture(rub_rx *h, const float *capture, ui
   const uint64_t L = c.L, acb_len = L * (c.nac * c.N + 4), tx_sig_len = (uint64_t)c.D * L, Wlen = acb_len + tx_sig_len;
   const uint32_t max_ac = c.nac * c.N, slots = max_ac + 1;
   if (c.c.estimator != RUB_EST_LS_FULLBAND) { set_error("process_capture: TDMA access codes only"); return RUB_ERR_UNSUPPORTED; }
-  if (n_samples >= 0x7fffffffull) { set_error("process_capture: capture longer than 2^31 samples"); return RUB_ERR_INVALID_ARG; }
-  if (max_frames == 0 || n_samples < Wlen) return RUB_OK;
+  const uint64_t lead = Wlen, n = n_samples + lead;   // padded row length
+  if (n >= 0x7fffffffull) { set_error("process_capture: capture longer than 2^31 samples"); return RUB_ERR_INVALID_ARG; }
+  if (c.N > 8) { set_error("process_capture: at most 8 streams"); return RUB_ERR_UNSUPPORTED; }
+  if (max_frames == 0 || n_samples < L) return RUB_OK;
   CUDA_TRY(cudaSetDevice(h->device));
-  // --- capture and metric on the device
-  cf *d_cap = nullptr;
-  float *d_y = nullptr;
-  CUDA_TRY(cudaMalloc(&d_cap, sizeof(cf) * n_samples * c.N));
-  struct Guard { std::vector<void *> p; ~Guard() { for (void *q : p) cudaFree(q); } } guard;
-  guard.p.push_back(d_cap);
-  CUDA_TRY(cudaMalloc(&d_y, sizeof(float) * n_samples * c.N));
-  guard.p.push_back(d_y);
-  CUDA_TRY(cudaMemcpyAsync(d_cap, capture, sizeof(cf) * n_samples * c.N, cudaMemcpyHostToDevice, h->stream));
+  // --- device scratch, carved from one grow-only allocation
+  const size_t pts = (size_t)c.N * c.D * c.Mo;
+  const size_t eq_b = (out->out_mask & RUB_OUT_EQ) ? pts * sizeof(cf) : 0, llr_b = (out->out_mask & RUB_OUT_LLR) ? pts * c.q * sizeof(float) : 0,
+               bits_b = (out->out_mask & RUB_OUT_BITS) ? (size_t)c.N * c.D * c.row_bytes : 0, rd_b = (out->out_mask & RUB_OUT_RXDATA) ? pts : 0,
+               g_b = (out->out_mask & RUB_OUT_G) ? (size_t)c.N * c.N * c.M * sizeof(cf) : 0, tx_b = out->tx_data ? pts : 0;
+  const bool sinks = !h->debug_dir.empty();
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  size_t need = 0;
+  auto carve = [&](size_t bytes) { const size_t o = need; need += al(bytes); return o; };
+  const size_t o_cap = carve(sizeof(cf) * n * c.N), o_y = carve(sizeof(float) * n * c.N), o_ok = carve(n * c.N),
+               o_off = carve(sizeof(long long) * max_frames), o_syn = carve(sizeof(unsigned long long) * max_frames), o_cnt = carve(256),
+               o_keys = carve(sizeof(unsigned long long) * (size_t)max_frames * c.N * slots),
+               o_tim = carve(sizeof(int32_t) * (size_t)max_frames * c.N * c.T), o_pay = carve(sizeof(int32_t) * max_frames),
+               o_eq = carve(eq_b * max_frames), o_llr = carve(llr_b * max_frames), o_bits = carve(bits_b * max_frames),
+               o_rd = carve(rd_b * max_frames), o_g = carve(g_b * max_frames), o_tx = carve(tx_b * max_frames),
+               o_corr = carve(sinks ? sizeof(float) * (size_t)c.N * slots * L : 0);
+  if (need > h->capt_bytes) {
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_capt);
+    h->d_capt = nullptr;
+    h->capt_bytes = 0;
+    if (cudaMalloc(&h->d_capt, need) != cudaSuccess) { cudaGetLastError(); set_error("out of device memory (%zu B of capture scratch)", need); return RUB_ERR_NOMEM; }
+    h->capt_bytes = need;
+  }
+  unsigned char *base = (unsigned char *)h->d_capt;
+  cf *d_cap = (cf *)(base + o_cap);
+  float *d_y = (float *)(base + o_y);
+  unsigned char *d_ok = base + o_ok;
+  long long *d_off = (long long *)(base + o_off);
+  unsigned long long *d_syn = (unsigned long long *)(base + o_syn), *d_keys = (unsigned long long *)(base + o_keys);
+  unsigned *d_cnt = (unsigned *)(base + o_cnt);
+  int32_t *d_tim = (int32_t *)(base + o_tim), *d_pay = (int32_t *)(base + o_pay);
+  // --- capture behind its zero lead-in, metric, plateau flags, the walk over the bursts
+  for (uint32_t s = 0; s < c.N; s++) {
+    CUDA_TRY(cudaMemsetAsync(d_cap + (size_t)s * n, 0, sizeof(cf) * lead, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_cap + (size_t)s * n + lead, reinterpret_cast<const cf *>(capture) + (size_t)s * n_samples,
+                             sizeof(cf) * n_samples, cudaMemcpyHostToDevice, h->stream));
+  }
+  CUDA_TRY(launch_sc_metric(h, h->sync_mode, d_cap, n, n, c.N, d_y));
   {
-    const size_t smem = (size_t)(c.M + c.M / 2 + 256) * sizeof(cf);
-    CUDA_TRY(cudaFuncSetAttribute(k_sc_metric, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    for (uint32_t s = 0; s < c.N; s++)
-      k_sc_metric<<<(unsigned)((n_samples + 255) / 256), 256, smem, h->stream>>>(d_cap + (size_t)s * n_samples, n_samples, (int)c.M,
-                                                                              d_y + (size_t)s * n_samples);
-    h->launches += c.N;
+    dim3 grid((unsigned)((n + 1023) / 1024), c.N);
+    k_plateau_ok<<<grid, 256, 0, h->stream>>>(d_y, n, n, (int)c.cp, threshold, d_ok);
+    PlateauWalk w;
+    w.n = (long long)n; w.L = (long long)L; w.acb_len = (long long)acb_len; w.tx_sig_len = (long long)tx_sig_len; w.Wlen = (long long)Wlen;
+    w.N = (int)c.N; w.cp = (int)c.cp; w.threshold = threshold; w.max_frames = max_frames;
+    k_plateau_walk<<<1, 1024, 0, h->stream>>>(d_ok, d_y, n, w, d_off, d_syn, d_cnt);
+    h->launches += 2;
     CUDA_TRY(cudaGetLastError());
   }
-  std::vector<float> y((size_t)n_samples * c.N);
-  CUDA_TRY(cudaMemcpyAsync(y.data(), d_y, sizeof(float) * y.size(), cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(cudaStreamSynchronize(h->stream));
-  // --- the plateau rule of execute_sc_sync (framing.cc:591-624) and the access-code buffering of
-  //     execute_save_access_codes (:639-651), restarted after every burst
-  std::vector<long long> win_off;
-  std::vector<uint64_t> syncs;
-  {
-    std::vector<uint64_t> pstart(c.N, 0), pend(c.N, 0);
-    std::vector<char> inpl(c.N, 0);
-    uint64_t i = 0;
-    while (i < n_samples && win_off.size() < max_frames) {
-      bool proceed = true;
-      for (uint32_t s = 0; s < c.N; s++) {
-        if (y[(size_t)s * n_samples + i] > threshold) {
-          if (inpl[s]) pend[s] = i;
-          else { inpl[s] = 1; pstart[s] = i; pend[s] = i; }
-        } else inpl[s] = 0;
-        proceed = proceed && (pend[s] - pstart[s] > c.cp) && inpl[s];
-      }
-      if (!proceed) { i++; continue; }
-      uint64_t si = 0;
-      for (uint32_t s = 0; s < c.N; s++) si += pstart[s];
-      si /= c.N;
-      const uint64_t i_switch = si + tx_sig_len + acb_len - L;  // first sample that is not buffered
-      if (i_switch > n_samples) break;                           // the burst runs past the capture
-      if (i_switch >= Wlen) { win_off.push_back((long long)(i_switch - Wlen)); syncs.push_back(si); }
-      std::fill(inpl.begin(), inpl.end(), 0);
-      i = i_switch + 1;
+  uint32_t F = 0;
+  CUDA_TRY(cudaMemcpyAsync(&F, d_cnt, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  std::vector<unsigned long long> syncs(max_frames);
+  CUDA_TRY(cudaMemcpyAsync(syncs.data(), d_syn, sizeof(unsigned long long) * max_frames, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));   // the burst count sizes the launches below
+  if (sinks) {
+    // f_sc_%d.dat (framing.cc:598-600): the metric of every capture sample of stream %d (1-based), float32
+    std::vector<float> yh((size_t)n_samples);
+    for (uint32_t s = 0; s < c.N; s++) {
+      CUDA_TRY(cudaMemcpy(yh.data(), d_y + (size_t)s * n + lead, sizeof(float) * n_samples, cudaMemcpyDeviceToHost));
+      rub_status ws = write_floats(h->debug_dir + "/f_sc_" + std::to_string(s + 1) + ".dat", yh.data(), yh.size());
+      if (ws) return ws;
     }
   }
-  const uint32_t F = (uint32_t)win_off.size();
   if (F == 0) return RUB_OK;
-  // --- batched timing search (framing.cc:702-744) straight from the capture rows
-  long long *d_off = nullptr;
-  unsigned long long *d_keys = nullptr;
-  CUDA_TRY(cudaMalloc(&d_off, sizeof(long long) * F));
-  guard.p.push_back(d_off);
-  CUDA_TRY(cudaMalloc(&d_keys, sizeof(unsigned long long) * (size_t)F * c.N * slots));
-  guard.p.push_back(d_keys);
-  CUDA_TRY(cudaMemcpyAsync(d_off, win_off.data(), sizeof(long long) * F, cudaMemcpyHostToDevice, h->stream));
+  // --- batched timing search (framing.cc:702-744) straight from the capture rows, tables on the device
   CUDA_TRY(cudaMemsetAsync(d_keys, 0, sizeof(unsigned long long) * (size_t)F * c.N * slots, h->stream));
   {
     const size_t smem = (size_t)(2 * c.M + 256) * sizeof(cf);
     CUDA_TRY(cudaFuncSetAttribute(k_timing_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((c.L + 255) / 256, c.N * slots, F);
-    k_timing_search<<<grid, 256, smem, h->stream>>>(d_cap, Wlen, n_samples, d_off, h->d_s1, nullptr, (int)c.M, (int)c.L,
-                                                    (int)c.N, (int)c.nac, d_keys);
-    h->launches += 1;
+    k_timing_search<<<grid, 256, smem, h->stream>>>(d_cap, Wlen, n, d_off, h->d_s1, nullptr, (int)c.M, (int)c.L,
+                                                    (int)c.N, (int)c.nac, d_keys, nullptr, 0.f);
+    const int tot = (int)(F * c.N * max_ac);
+    k_timing_tables<<<(tot + 255) / 256, 256, 0, h->stream>>>(d_keys, d_off, (int)F, (int)c.N, (int)max_ac, (int)c.L, (int)c.M, d_tim, d_pay);
+    h->launches += 2;
     CUDA_TRY(cudaGetLastError());
   }
-  std::vector<unsigned long long> keys((size_t)F * c.N * slots);
-  CUDA_TRY(cudaMemcpyAsync(keys.data(), d_keys, sizeof(unsigned long long) * keys.size(), cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(cudaStreamSynchronize(h->stream));
-  std::vector<int32_t> timing((size_t)F * c.N * c.T), pay(F);
-  for (uint32_t f = 0; f < F; f++) {
+  if (sinks) {
+    // corr_%d_%d.dat (framing.cc:676-680, :873-883): per rx stream (1-based) and access code (1-based; 0 = the S0
+    // preamble when rub_rx_set_S0 was called) a float32 array of access_code_buffer_len - M correlation powers,
+    // non-zero at the candidate offsets i + symbol_len * ac_id, of the LAST burst (the reference reopens the files
+    // for every burst)
+    float *d_corr = (float *)(base + o_corr);
+    unsigned long long *d_k2 = d_keys + (size_t)F * c.N * slots - (size_t)c.N * slots;  // rewrite the last burst's keys: same values
+    const size_t smem = (size_t)(2 * c.M + 256) * sizeof(cf);
+    dim3 grid((c.L + 255) / 256, c.N * slots, 1);
+    CUDA_TRY(cudaMemsetAsync(d_corr, 0, sizeof(float) * (size_t)c.N * slots * L, h->stream));
+    k_timing_search<<<grid, 256, smem, h->stream>>>(d_cap, Wlen, n, d_off + (F - 1), h->d_s1, h->d_s0, (int)c.M, (int)c.L,
+                                                    (int)c.N, (int)c.nac, d_k2, d_corr, h->s0_corr_scale);
+    h->launches += 1;
+    std::vector<float> ch((size_t)c.N * slots * L), file(acb_len - c.M);
+    CUDA_TRY(cudaMemcpyAsync(ch.data(), d_corr, sizeof(float) * ch.size(), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
     for (uint32_t r = 0; r < c.N; r++)
-      for (uint32_t ac = 0; ac < max_ac; ac++) {
-        const unsigned long long k = keys[((size_t)f * c.N + r) * slots + ac + 1];
-        const uint32_t idx = (k >> 32) ? (uint32_t)(c.L * (ac + 1)) + (0xffffffffu - (uint32_t)(k & 0xffffffffu)) : 0u;
-        timing[((size_t)f * c.N + r) * c.T + ac] = (int32_t)(win_off[f] + idx);
+      for (uint32_t slot = 0; slot < slots; slot++) {
+        if (slot == 0 && !h->d_s0) continue;
+        std::fill(file.begin(), file.end(), 0.f);
+        const size_t off = (size_t)L * slot;   // slot 0 (S0): offsets [0, L); access code a: i + L * (a + 1)
+        for (uint32_t i = 0; i < L && off + i < file.size(); i++) file[off + i] = ch[((size_t)r * slots + slot) * L + i];
+        rub_status ws = write_floats(h->debug_dir + "/corr_" + std::to_string(r + 1) + "_" + std::to_string(slot) + ".dat", file.data(), file.size());
+        if (ws) return ws;
       }
-    // payload start from rx stream 1's last access code (quirk Q4, framing.cc:857)
-    pay[f] = timing[((size_t)f * c.N + (c.N > 1 ? 1 : 0)) * c.T + max_ac - 1] + (int32_t)c.M;
   }
   // --- LS / invert / decode of all bursts in one batch, outputs gathered on the device
-  const size_t pts = (size_t)c.N * c.D * c.Mo;
-  const size_t eq_b = pts * sizeof(cf), llr_b = pts * c.q * sizeof(float), bits_b = (size_t)c.N * c.D * c.row_bytes,
-               rd_b = pts, g_b = (size_t)c.N * c.N * c.M * sizeof(cf), tx_b = pts;
-  int32_t *d_tim = nullptr, *d_pay = nullptr;
-  CUDA_TRY(cudaMalloc(&d_tim, sizeof(int32_t) * timing.size())); guard.p.push_back(d_tim);
-  CUDA_TRY(cudaMalloc(&d_pay, sizeof(int32_t) * F)); guard.p.push_back(d_pay);
-  CUDA_TRY(cudaMemcpyAsync(d_tim, timing.data(), sizeof(int32_t) * timing.size(), cudaMemcpyHostToDevice, h->stream));
-  CUDA_TRY(cudaMemcpyAsync(d_pay, pay.data(), sizeof(int32_t) * F, cudaMemcpyHostToDevice, h->stream));
   rub_rx_io d;
   memset(&d, 0, sizeof(d));
   d.iq = reinterpret_cast<const float *>(d_cap);
-  d.layout.rx_stride = n_samples;
+  d.layout.rx_stride = n;
   d.timing = d_tim;
   d.payload_start = d_pay;
   d.out_mask = out->out_mask;
-  auto dev_out = [&](size_t bytes, void **p) -> rub_status { CUDA_TRY(cudaMalloc(p, bytes * F)); guard.p.push_back(*p); return RUB_OK; };
-  rub_status st = RUB_OK;
-  if (!st && (out->out_mask & RUB_OUT_EQ)) st = dev_out(eq_b, (void **)&d.eq);
-  if (!st && (out->out_mask & RUB_OUT_LLR)) st = dev_out(llr_b, (void **)&d.llr);
-  if (!st && (out->out_mask & RUB_OUT_BITS)) st = dev_out(bits_b, (void **)&d.bits);
-  if (!st && (out->out_mask & RUB_OUT_RXDATA)) st = dev_out(rd_b, (void **)&d.rx_data);
-  if (!st && (out->out_mask & RUB_OUT_G)) st = dev_out(g_b, (void **)&d.G);
-  if (!st && out->tx_data) {
-    uint8_t *dtx = nullptr;
-    st = dev_out(tx_b, (void **)&dtx);
-    if (!st) { CUDA_TRY(cudaMemcpyAsync(dtx, out->tx_data, tx_b * F, cudaMemcpyHostToDevice, h->stream)); d.tx_data = dtx; }
+  if (eq_b) d.eq = (float *)(base + o_eq);
+  if (llr_b) d.llr = (float *)(base + o_llr);
+  if (bits_b) d.bits = base + o_bits;
+  if (rd_b) d.rx_data = base + o_rd;
+  if (g_b) d.G = (float *)(base + o_g);
+  if (tx_b) {
+    CUDA_TRY(cudaMemcpyAsync(base + o_tx, out->tx_data, tx_b * F, cudaMemcpyHostToDevice, h->stream));
+    d.tx_data = base + o_tx;
   }
+  rub_status st = process_device(h, &d, F, false, /*shared_rows=*/true);
   if (st) return st;
-  st = process_device(h, &d, F, false, /*shared_rows=*/true);
-  if (st) return st;
-  if (d.eq) CUDA_TRY(cudaMemcpyAsync(out->eq, d.eq, eq_b * F, cudaMemcpyDeviceToHost, h->stream));
-  if (d.llr) CUDA_TRY(cudaMemcpyAsync(out->llr, d.llr, llr_b * F, cudaMemcpyDeviceToHost, h->stream));
-  if (d.bits) CUDA_TRY(cudaMemcpyAsync(out->bits, d.bits, bits_b * F, cudaMemcpyDeviceToHost, h->stream));
-  if (d.rx_data) CUDA_TRY(cudaMemcpyAsync(out->rx_data, d.rx_data, rd_b * F, cudaMemcpyDeviceToHost, h->stream));
-  if (d.G) CUDA_TRY(cudaMemcpyAsync(out->G, d.G, g_b * F, cudaMemcpyDeviceToHost, h->stream));
+  if (eq_b) CUDA_TRY(cudaMemcpyAsync(out->eq, d.eq, eq_b * F, cudaMemcpyDeviceToHost, h->stream));
+  if (llr_b) CUDA_TRY(cudaMemcpyAsync(out->llr, d.llr, llr_b * F, cudaMemcpyDeviceToHost, h->stream));
+  if (bits_b) CUDA_TRY(cudaMemcpyAsync(out->bits, d.bits, bits_b * F, cudaMemcpyDeviceToHost, h->stream));
+  if (rd_b) CUDA_TRY(cudaMemcpyAsync(out->rx_data, d.rx_data, rd_b * F, cudaMemcpyDeviceToHost, h->stream));
+  if (g_b) CUDA_TRY(cudaMemcpyAsync(out->G, d.G, g_b * F, cudaMemcpyDeviceToHost, h->stream));
   if (out->counters) CUDA_TRY(cudaMemcpyAsync(out->counters, h->d_counters, sizeof(uint64_t) * 4 * c.N, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
-  if (sync_index) for (uint32_t f = 0; f < F; f++) sync_index[f] = syncs[f];
+  if (sync_index) for (uint32_t f = 0; f < F; f++) sync_index[f] = syncs[f] - lead;   // capture coordinates
   *n_found = F;
   return RUB_OK;
 }

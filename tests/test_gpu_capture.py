@@ -67,3 +67,77 @@ def test_capture_without_bursts_and_truncated_burst():
     assert n == 1 and np.array_equal(out["rx_data"][0], tx[0])
     # max_frames bounds the search
     assert rx.process_capture(cap, max_frames=1)[0] == 1
+
+
+@pytest.mark.parametrize("mode", [rub.SYNC_FIR, rub.SYNC_SCAN])
+def test_both_metric_forms_find_and_decode_the_same_bursts(mode):
+    """process_capture with the bit-exact FIR metric and with the sliding-sum metric (row f2): same bursts, same
+    equalised symbols bit for bit (the timing search pins the FFT windows, not the plateau start), plateau starts
+    within a sample of the oracle's."""
+    cfg = rub.preset("C1", M=256, cp_len=20, num_access_codes=4, num_data_symbols=25)
+    K = 4
+    S0, S1, cap, tx, slices = _bursts(cfg, K, seed=0xF2, gaps=[11, 0, 250])
+    rx = rub.Receiver(cfg, S1)
+    rx.set_sync_mode(mode)
+    n, sync, out = rx.process_capture(cap, max_frames=K + 2, out_mask=rub.OUT_EQ | rub.OUT_RXDATA, tx_data=tx)
+    assert n == K and np.array_equal(out["rx_data"], tx)
+    for k, (a, b) in enumerate(slices):
+        r = orc.framesync_execute(to_orc(cfg), S0, S1, cap[:, a:b])
+        assert abs(int(sync[k]) - (a + int(r["sync_index"]))) <= (1 if mode == rub.SYNC_FIR else 2)
+        assert np.array_equal(out["eq"][k], r["eq"])
+
+
+def test_burst_at_the_very_start_of_a_capture_is_decoded():
+    """Round-1 ADVICE: a plateau found before a whole window of samples had been seen was dropped.  The
+    reference's window buffer is zero-filled in front of the first sample; so is the device copy now."""
+    cfg = rub.preset("C1", M=64, cp_len=16, num_access_codes=20, num_data_symbols=40)
+    S0, S1, cap, tx, slices = _bursts(cfg, 1, seed=77)
+    lead = (cfg.nac * cfg.N + 1) * cfg.L
+    early = np.ascontiguousarray(cap[:, lead - 40:])          # S0 starts 40 samples into the capture
+    rx = rub.Receiver(cfg, S1)
+    rx.set_sync_mode(rub.SYNC_FIR)
+    n, sync, out = rx.process_capture(early, max_frames=2, out_mask=rub.OUT_EQ | rub.OUT_RXDATA, tx_data=tx)
+    r = orc.framesync_execute(to_orc(cfg), S0, S1, early)
+    assert r["rc"] == 0 and n == 1
+    assert int(sync[0]) == int(r["sync_index"])
+    assert np.array_equal(out["eq"][0], r["eq"])
+    assert np.array_equal(out["rx_data"][0], tx[0])
+
+
+def test_debug_sinks_have_the_reference_formats(tmp_path):
+    """Row f3: f_sc_%d.dat and corr_%d_%d.dat (mimo/framing.cc:598-600, :676-680, :873-883), float32, readable the way
+    mimo/apps/plot.py:27-40 reads them, holding the oracle's values."""
+    cfg = rub.preset("C1", M=64, cp_len=16, num_access_codes=4, num_data_symbols=12)
+    S0, S1, cap, tx, slices = _bursts(cfg, 2, seed=0xF3)
+    s0 = rub.default_S0(cfg)[1]
+    rx = rub.Receiver(cfg, S1)
+    rx.set_S0(s0)
+    rx.set_sync_mode(rub.SYNC_FIR)
+    rx.set_debug_dir(tmp_path)
+    n, sync, out = rx.process_capture(cap, max_frames=4)
+    assert n == 2
+    L, M, N = cfg.L, cfg.M, cfg.N
+    max_ac = cfg.nac * N
+    acb_len = L * (max_ac + 4)
+    for s in range(N):
+        y = np.fromfile(tmp_path / f"f_sc_{s + 1}.dat", np.float32)
+        ref = orc.sc_metric(M, cap[s])
+        assert y.size == cap.shape[1] and np.array_equal(y.view(np.uint32), ref.view(np.uint32))
+    # the last burst's window as the reference holds it when estimate_channel runs
+    Wlen = acb_len + cfg.D * L
+    i_switch = int(sync[1]) + cfg.D * L + acb_len - L
+    win = cap[:, i_switch - Wlen:i_switch]
+    for r in range(N):
+        for a in range(0, max_ac + 1):
+            v = np.fromfile(tmp_path / f"corr_{r + 1}_{a}.dat", np.float32)
+            assert v.size == acb_len - M
+            tpl = S0 if a == 0 else S1[(a - 1) % N, (a - 1) // N]
+            base = 0 if a == 0 else L * a
+            nz = np.nonzero(v)[0]
+            assert nz.min() >= base and nz.max() < base + L
+            for i in (0, 1, L // 2, L - 1):                       # the reference's way: one FFT per candidate offset
+                X = orc.fft_forward(win[r, base + i: base + i + M])
+                xyz = np.sum(X.astype(np.complex128) * np.conj(tpl.astype(np.complex128)))
+                want = abs(xyz) ** 2 / float(M * M)
+                assert abs(v[base + i] - want) <= 1e-4 * max(want, np.abs(v).max() * 1e-3)
+            assert int(np.argmax(v)) == base + int(np.argmax(v[base:base + L]))

@@ -39,6 +39,27 @@ def test_sc_metric_is_bit_exact(name, D, over):
     assert rx.launch_count == cfg.N
 
 
+def test_scan_metric_tracks_the_fir_metric():
+    """Row f2: the sliding-sum form (O(1) per sample) agrees with the bit-exact FIR form to fp32 rounding and
+    crosses the plateau threshold within a sample of it."""
+    cfg, S0, s0, S1, cap, tx, lead = _capture("C1", 6, 0x5D, M=1024, cp_len=72, num_access_codes=2)
+    rx = rub.Receiver(cfg, S1)
+    for s in range(cfg.N):
+        x = cap[s]
+        yf, ys = rx.sc_metric(x, rub.SYNC_FIR), rx.sc_metric(x, rub.SYNC_SCAN)
+        ok = np.isfinite(yf) & np.isfinite(ys) & (np.arange(x.size) > lead)
+        assert ok.sum() > x.size // 2
+        assert np.abs(ys[ok] - yf[ok]).max() <= 2e-4 * max(1.0, np.abs(yf[ok]).max())
+        cf_, cs_ = np.nonzero(yf > 0.95)[0], np.nonzero(ys > 0.95)[0]
+        assert cf_.size and abs(int(cf_[0]) - int(cs_[0])) <= 1
+    # tile boundaries and ragged lengths: every length runs and the defined values agree
+    rng = np.random.default_rng(3)
+    for n in (1, 255, 2047, 2048, 2049, 5000):
+        x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+        yf, ys = rx.sc_metric(x, rub.SYNC_FIR), rx.sc_metric(x, rub.SYNC_SCAN)
+        assert np.allclose(ys, yf, rtol=2e-4, atol=1e-6), n
+
+
 def test_sc_metric_ragged_lengths():
     cfg = rub.preset("C1", num_data_symbols=1, M=64, cp_len=16, num_access_codes=2)
     S1, _ = rub.default_S1(cfg)
