@@ -255,6 +255,7 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
         const int u = ug - f * TU;
         c = u % nac; r0 = (u / nac) % N; t = u / (nac * N);
         buf = land + (size_t)(ug & 1) * PAD;
+
         // the G scratch is free once the weights of the previous frame have been computed from it
         if (u == 0 && f >= 1) mbar_wait(&mbar[7], (unsigned)((f - 1) & 1));
         mbar_wait(&mbar[4 + (ug & 1)], (unsigned)((ug >> 1) & 1));
@@ -291,8 +292,11 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
       for (int r = 0; r < nr; r++) {
         cf *reg = buf + (size_t)r * PAD;
         FF::S2::template load<true>(ft, reg, v);
+        // training: the landing slot is about to be refilled by the async proxy (TMA).  A barrier only orders
+        // the ISSUE of these loads; the proxy fence waits until they have been performed (they may still sit in
+        // another scheduler's LSU queue when thread 0 gets to issue the copy).
+        if (training) fence_async_smem();
         named_bar(1, NT);
-        // training: every thread has read the landing slot, refill it with the unit two ahead
         if (training && tid == 0) issue_training(ug + 2);
         FF::S2::compute_pre(v, tw);
         if (!training) FF::S2::template store<false, true>(ft, v, reg, a.dn);
@@ -329,12 +333,14 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
 #pragma unroll
             for (int t2 = 0; t2 < R2; t2++) {
               const int j = ft + b * NT, k = (j / NS2) * NS2 * R2 + (j % NS2) + t2 * NS2;
-              Gf[k] = mk(acc[b * R2 + t2].x, acc[b * R2 + t2].y);
+              st_hint2(Gf + k, acc[b * R2 + t2], pol_stream);
             }
         }
         ug++;
         if (ug - f * TU == TU) {
-          // G(f) complete: every lane's stores are ordered before lane 0's release-arrive
+          // G(f) complete.  The detect warps read it from L2 (L1::no_allocate loads): a CTA-scope release does not
+          // wait for global stores to get there, so every thread fences its own stores at GPU scope first
+          __threadfence();
           __syncwarp();
           if (lane == 0) mbar_arrive(&mbar[6]);
         }
