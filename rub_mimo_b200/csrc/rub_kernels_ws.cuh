@@ -104,12 +104,12 @@ __device__ __forceinline__ void ws_dot(const TaskRegs<N> &t, const float4 *y4, c
   z0 = cscale(wy_dot<N>(w0, y0), t.g.x);
   z1 = cscale(wy_dot<N>(w1, y1), t.g.y);
 }
-// the rest of the task: slicer, max-log LLRs (staged in [k][bit] order at lp), packed bits; returns the two
-// demodulated symbols (sym0 | sym1 << 8)
+// hard decisions of the task: equalised symbols out, slicer, packed bits; returns the two demodulated symbols
+// (sym0 | sym1 << 8).  Runs BEFORE the next task's W loads are requested: its warp shuffles must not share a
+// scoreboard with loads that take an L2 round trip.
 template <int MB>
-__device__ __forceinline__ unsigned ws_demap(const ChainArgs &a, const DemapConst &dc, const float *refs, cf z0, cf z1, float2 is,
-                                             long long o, float *lp, unsigned short *bp, unsigned long long pol_stream,
-                                             int lane) {
+__device__ __forceinline__ unsigned ws_hard(const ChainArgs &a, const float *refs, cf z0, cf z1, long long o,
+                                            unsigned short *bp, unsigned long long pol_stream, int lane) {
   constexpr int Q = 2 * MB;
   if (a.eq) st_hint4(a.eq + o, make_float4(z0.x, z0.y, z1.x, z1.y), pol_stream);
   const unsigned si0 = slice_axis_refs<MB>(z0.x, refs), sq0 = slice_axis_refs<MB>(z0.y, refs);
@@ -117,17 +117,6 @@ __device__ __forceinline__ unsigned ws_demap(const ChainArgs &a, const DemapCons
   // (gray(si) << MB) | gray(sq) in one pass: the bit shifted from si into sq's top position is masked off
   const unsigned c0 = (si0 << MB) | sq0, c1 = (si1 << MB) | sq1;
   const unsigned sym0 = c0 ^ ((c0 >> 1) & ~(1u << (MB - 1))), sym1 = c1 ^ ((c1 >> 1) & ~(1u << (MB - 1)));
-  if (a.llr) {
-    float l[2 * Q];  // [k][bit] order
-    const float k0 = dc.k4 * is.x, k1 = dc.k4 * is.y;
-    llr_axis<MB>(z0.x, k0, dc, l);
-    llr_axis<MB>(z0.y, k0, dc, l + MB);
-    llr_axis<MB>(z1.x, k1, dc, l + Q);
-    llr_axis<MB>(z1.y, k1, dc, l + Q + MB);
-#pragma unroll
-    for (int v = 0; v < 2 * Q / 4; v++)
-      *reinterpret_cast<float4 *>(lp + 4 * v) = make_float4(l[4 * v], l[4 * v + 1], l[4 * v + 2], l[4 * v + 3]);
-  }
   const unsigned rx2 = sym0 | (sym1 << 8);
   if (a.rx_data) *reinterpret_cast<unsigned short *>(a.rx_data + o) = (unsigned short)rx2;
   if (a.bits) {
@@ -146,6 +135,20 @@ __device__ __forceinline__ unsigned ws_demap(const ChainArgs &a, const DemapCons
     }
   }
   return rx2;
+}
+// max-log LLRs of the task, staged in [k][bit] order at lp
+template <int MB>
+__device__ __forceinline__ void ws_llr(const DemapConst &dc, cf z0, cf z1, float2 is, float *lp) {
+  constexpr int Q = 2 * MB;
+  float l[2 * Q];  // [k][bit] order
+  const float k0 = dc.k4 * is.x, k1 = dc.k4 * is.y;
+  llr_axis<MB>(z0.x, k0, dc, l);
+  llr_axis<MB>(z0.y, k0, dc, l + MB);
+  llr_axis<MB>(z1.x, k1, dc, l + Q);
+  llr_axis<MB>(z1.y, k1, dc, l + Q + MB);
+#pragma unroll
+  for (int v = 0; v < 2 * Q / 4; v++)
+    *reinterpret_cast<float4 *>(lp + 4 * v) = make_float4(l[4 * v], l[4 * v + 1], l[4 * v + 2], l[4 * v + 3]);
 }
 
 template <int LOG2M, int N, int MB>
@@ -264,6 +267,10 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
         buf = ring + (size_t)(pg & 1) * TR::BUF_ELEMS;
         mbar_wait(&mbar[pg & 1], (unsigned)((pg >> 1) & 1));
       }
+      // training: the sign bytes of this thread's carriers (one per last-stage butterfly), requested early
+      unsigned sgb[B2];
+#pragma unroll
+      for (int b = 0; b < B2; b++) sgb[b] = training ? (unsigned)fa.sgn8[((size_t)t * nac + c) * (M / R2) + ft + b * NT] : 0u;
       // In place, stage by stage over the job's antennas; the twiddles of a stage depend on the thread only
       // and are read once per job.  The barrier between a pair's loads and its stores also orders the stores
       // of the previous pair before the next stage's loads of that antenna (N >= 2 pairs later); a one-antenna
@@ -292,13 +299,14 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
       for (int r = 0; r < nr; r++) {
         cf *reg = buf + (size_t)r * PAD;
         FF::S2::template load<true>(ft, reg, v);
-        // training: the landing slot is about to be refilled by the async proxy (TMA).  A barrier only orders
-        // the ISSUE of these loads; the proxy fence waits until they have been performed (they may still sit in
-        // another scheduler's LSU queue when thread 0 gets to issue the copy).
-        if (training) fence_async_smem();
+        FF::S2::compute_pre(v, tw);
+        // The barrier orders every thread's loads of the region before any store into it (payload: the in-place
+        // stores below; training: the TMA refill of the landing slot).  It sits AFTER the butterflies on purpose:
+        // a barrier only orders the issue of loads, and a load still queued in another scheduler's LSU pipe
+        // can be overtaken by the async proxy; having consumed the loaded values, every thread's loads have been
+        // performed when it arrives.
         named_bar(1, NT);
         if (training && tid == 0) issue_training(ug + 2);
-        FF::S2::compute_pre(v, tw);
         if (!training) FF::S2::template store<false, true>(ft, v, reg, a.dn);
       }
       if (!training) {
@@ -316,7 +324,7 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
         const float dinit = (q1 && r0 == t) ? 1.0f : 0.0f;
 #pragma unroll
         for (int b = 0; b < B2; b++) {
-          const unsigned sb = fa.sgn8[((size_t)t * nac + c) * (M / R2) + ft + b * NT];
+          const unsigned sb = sgb[b];
 #pragma unroll
           for (int t2 = 0; t2 < R2; t2++) {
             const int i = b * R2 + t2;
@@ -463,19 +471,18 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
           const unsigned tx2 = txv;
           const long long oc = o, boc = bo;
           ws_dot<N>(w, y4, z0, z1);
-          // W of the next task lands in the registers the products just released
+          const unsigned rx2 = ws_hard<MB>(a, refs, z0, z1, oc, reinterpret_cast<unsigned short *>(a.bits + boc + (lane >> 2) * Q),
+                                           pol_stream, lane);
+          // W of the next task lands in the registers the products released
           if (s + 1 < N) { wp += N * M; gp += M; o += DM; bo += bo_s; }
           else { wp += KSTEP - (N - 1) * N * M; gp += KSTEP - (N - 1) * M; o += (long long)KSTEP - (N - 1) * DM; bo += bo_k; }
           if (it + 1 < KPW * N) load_w();
-          unsigned char *slot = slot0 + (it & 1) * stage_stride;
           if (a.llr) {
+            unsigned char *slot = slot0 + (it & 1) * stage_stride;
             // the bulk store issued two tasks ago from this staging slot must have drained
             if (lane == 0) bulk_wait_read<1>();
             __syncwarp();
-          }
-          const unsigned rx2 = ws_demap<MB>(a, dc, refs, z0, z1, is, oc, reinterpret_cast<float *>(slot) + lane * 2 * Q,
-                                            reinterpret_cast<unsigned short *>(a.bits + boc + (lane >> 2) * Q), pol_stream, lane);
-          if (a.llr) {
+            ws_llr<MB>(dc, z0, z1, is, reinterpret_cast<float *>(slot) + lane * 2 * Q);
             fence_async_smem();
             __syncwarp();
             if (lane == 0) {
