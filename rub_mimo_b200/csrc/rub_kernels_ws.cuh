@@ -49,13 +49,16 @@ struct WsTraits {
   static constexpr int LAUNCH_REGS = 65536 / THREADS / 8 * 8;
   static constexpr int DET_REGS = LAUNCH_REGS - 8;
   static constexpr int FFT_REGS = (LAUNCH_REGS + 8 * DET_THREADS / NT) / 8 * 8;
+  // last-stage twiddles of a thread's FIRST butterfly (k < NT) live in shared memory, the rest of the table does
+  // not fit and is read from global memory while the first butterfly is computed
+  static constexpr int TW2S = (Fft<LOG2M>::S2::P / Fft<LOG2M>::S2::B - 1) * NT;
   static_assert(PL::NSTG == 3, "three-stage plans only");
   static_assert(NT % 128 == 0 && DET_THREADS % 128 == 0, "roles are whole warpgroups (setmaxnreg)");
   static_assert(N >= 2 && N <= 4, "FFT barrier scheme needs two antenna regions; packed counters hold four streams");
   static_assert(KPW * DET_WARPS == BLOCKS, "block split");
   static size_t smem_bytes(int q) {
     return (size_t)2 * BUF_ELEMS * sizeof(cf) /* payload ring */ + (size_t)2 * PAD * sizeof(cf) /* training landing pair */ +
-           (size_t)DET_WARPS * 2 * (256 * q) /* LLR staging */ + (size_t)FftTw<LOG2M>::CNT1 * sizeof(cf) /* stage-1 twiddles */ +
+           (size_t)DET_WARPS * 2 * (256 * q) /* LLR staging */ + (size_t)(FftTw<LOG2M>::CNT1 + TW2S) * sizeof(cf) /* stage-1 twiddles, first-butterfly half of stage 2 */ +
            128 /* mbarriers, counters */;
   }
 };
@@ -167,7 +170,8 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
   // mbarriers: full[2] (ring slot loaded), yrdy[2] (ring slot transformed), tfull[2] (landing slot loaded),
   // gdone at 6 (a frame's G is complete), wdone at 7 (the weights of a frame are computed)
   cf *tw_s = reinterpret_cast<cf *>(stage_base + (size_t)DET_WARPS * 2 * stage_stride);  // stage-1 twiddles, copied once
-  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(tw_s + TW::CNT1);
+  cf *tw2_s = tw_s + TW::CNT1;                                                            // stage 2, k < NT: [(t-1)*NT + k]
+  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(tw2_s + TR::TW2S);
   unsigned *done = reinterpret_cast<unsigned *>(mbar + 8);           // detect warps done with ring slot [2]
 
   const int tid = threadIdx.x;
@@ -224,6 +228,7 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
     issue_payload(1);
   }
   for (int i = tid; i < TW::CNT1; i += TR::THREADS) tw_s[i] = a.tw[TW::OFF1 + i];
+  for (int i = tid; i < TR::TW2S; i += TR::THREADS) tw2_s[i] = a.tw[TW::OFF2 + (i / NT) * TW::NS2 + i % NT];
   __syncthreads();
 
   if (warp < TR::FFT_WARPS) {
@@ -293,7 +298,13 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
         FF::S1::compute_pre(v, tw);
         FF::S1::template store<true, false>(ft, v, reg, 1.f);
       }
-      FF::S2::load_twiddles(ft, a.tw + TW::OFF2, tw);
+      // last-stage twiddles: tw[b * (R2 - 1) + t - 1] = table[(t - 1) * NS2 + ft + b * NT]; butterfly 0 from shared
+      // memory, the others from global memory
+#pragma unroll
+      for (int b = 0; b < B2; b++)
+#pragma unroll
+        for (int t2 = 1; t2 < R2; t2++)
+          tw[b * (R2 - 1) + t2 - 1] = (b == 0) ? tw2_s[(t2 - 1) * NT + ft] : a.tw[TW::OFF2 + (t2 - 1) * NS2 + (ft + b * NT) % NS2];
       if (training) named_bar(1, NT);
 #pragma unroll 1
       for (int r = 0; r < nr; r++) {
