@@ -173,6 +173,7 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
   cf *tw2_s = tw_s + TW::CNT1;                                                            // stage 2, k < NT: [(t-1)*NT + k]
   unsigned long long *mbar = reinterpret_cast<unsigned long long *>(tw2_s + TR::TW2S);
   unsigned *done = reinterpret_cast<unsigned *>(mbar + 8);           // detect warps done with ring slot [2]
+  volatile unsigned *sched = done + 2;                                // FFT warps: verdict of the work-conserving test
 
   const int tid = threadIdx.x;
   int lane;  // kept in a register: ptxas would otherwise re-read SR_TID.X (a long-latency S2R) at every use
@@ -250,9 +251,22 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
     // of the next frame that are due are worked off.
     int pg = -1;  // current payload symbol number (-1: prologue, the training units of the first frame)
     while (true) {
-      const bool training = ug < target;
+      bool training = ug < target;
       if (!training) {
-        if (++pg >= nf * D) break;
+        const int nx = pg + 1;
+        if (nx >= nf * D) break;
+        // Work conserving: if the ring slot of the next payload symbol is not loaded yet (the detect warps are
+        // behind) and training units of the next frame are left, work one off instead of waiting.  From the third
+        // payload symbol of a frame on the G scratch is known to be free (see the quota below).  Thread 0 tests
+        // the mbarrier, the group barrier publishes its verdict.
+        const int fn = nx / D, dn = nx - fn * D;
+        if (dn >= 2 && ug < (fn + 2) * TU && ug < nf * TU) {
+          if (tid == 0) *sched = mbar_test_wait(&mbar[nx & 1], (unsigned)((nx >> 1) & 1)) ? 0u : 1u;
+          named_bar(1, NT);
+          training = *sched != 0u;
+          named_bar(1, NT);  // everyone has read the verdict before thread 0 can overwrite it
+        }
+        if (!training) pg = nx;
       }
       cf v[FF::PTS], tw[FF::S1::NTW > FF::S2::NTW ? FF::S1::NTW : FF::S2::NTW];
       const int nr = training ? 1 : N;
