@@ -78,7 +78,7 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_power_cap,power.limit")
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
@@ -104,7 +104,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for r in self.rows:
             p = [x.strip() for x in r.split(",")]
             if len(p) < 8:
@@ -113,11 +113,18 @@ class ClockSampler:
                 sm.append(float(p[1])); mx.append(float(p[2]))
             except ValueError:
                 continue
+            try:
+                pw.append(float(p[3]))
+                if len(p) > 8:
+                    self.power_limit = float(p[8])
+            except ValueError:
+                pass
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "power_w": float(np.median(pw)) if pw else None,
+                "power_max_w": max(pw) if pw else None, "power_limit_w": getattr(self, "power_limit", None)}
 
 
 def _bind_to_gpu_cpus(dev_index):

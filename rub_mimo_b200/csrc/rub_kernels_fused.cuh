@@ -71,6 +71,12 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// A consumer that is expected to wait for a while (the detect warps waiting for the FFT warps): a bare
+// try_wait loop returns after a few cycles and its polling takes issue slots from the very warps it waits for
+// (measured: a quarter of the kernel's issued instructions), so sleep between polls.
+__device__ __forceinline__ void mbar_wait_backoff(unsigned long long *bar, unsigned parity, unsigned ns) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
 // L2 eviction policies: streams are read/written once (evict_first), the per-CTA W scratch
 // is re-read D times per frame (evict_last)
 __device__ __forceinline__ unsigned long long policy_evict_first() {

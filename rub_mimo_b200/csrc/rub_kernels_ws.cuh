@@ -29,6 +29,19 @@
 
 #include "rub_kernels_fused.cuh"
 
+#ifndef RUB_WS_ABLATE
+#define RUB_WS_ABLATE 0  // 1: FFT warps skip the transform, 2: detect warps skip detection (tools/dev only)
+#endif
+#ifndef RUB_WS_NOTX
+#define RUB_WS_NOTX 0  // measurement only: no tx_data loads (wrong counters)
+#endif
+#ifndef RUB_WS_GPOL
+#define RUB_WS_GPOL 0
+#endif
+#ifndef RUB_WS_BACKOFF_NS
+#define RUB_WS_BACKOFF_NS 100
+#endif
+
 namespace rub {
 
 template <int LOG2M, int N>
@@ -49,17 +62,15 @@ struct WsTraits {
   static constexpr int LAUNCH_REGS = 65536 / THREADS / 8 * 8;
   static constexpr int DET_REGS = LAUNCH_REGS - 8;
   static constexpr int FFT_REGS = (LAUNCH_REGS + 8 * DET_THREADS / NT) / 8 * 8;
-  // last-stage twiddles of a thread's FIRST butterfly (k < NT) live in shared memory, the rest of the table does
-  // not fit and is read from global memory while the first butterfly is computed
-  static constexpr int TW2S = (Fft<LOG2M>::S2::P / Fft<LOG2M>::S2::B - 1) * NT;
+  static constexpr int WREC = N * 64;                           // W record of one detection task: [r][64 carriers]
   static_assert(PL::NSTG == 3, "three-stage plans only");
   static_assert(NT % 128 == 0 && DET_THREADS % 128 == 0, "roles are whole warpgroups (setmaxnreg)");
   static_assert(N >= 2 && N <= 4, "FFT barrier scheme needs two antenna regions; packed counters hold four streams");
   static_assert(KPW * DET_WARPS == BLOCKS, "block split");
   static size_t smem_bytes(int q) {
-    return (size_t)2 * BUF_ELEMS * sizeof(cf) /* payload ring */ + (size_t)2 * PAD * sizeof(cf) /* training landing pair */ +
-           (size_t)DET_WARPS * 2 * (256 * q) /* LLR staging */ + (size_t)(FftTw<LOG2M>::CNT1 + TW2S) * sizeof(cf) /* stage-1 twiddles, first-butterfly half of stage 2 */ +
-           128 /* mbarriers, counters */;
+    return (size_t)2 * BUF_ELEMS * sizeof(cf) /* payload ring */ + (size_t)(M + PAD) * sizeof(cf) /* training: landing + work row */ +
+           (size_t)DET_WARPS * (256 * q) /* LLR staging */ + (size_t)DET_WARPS * WREC * sizeof(cf) /* W records, one per detect warp */ +
+           (size_t)(8 + DET_WARPS) * 8 + 16 /* mbarriers, counters */;
   }
 };
 
@@ -164,15 +175,16 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
   const ChainArgs &a = fa.a;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   cf *ring = reinterpret_cast<cf *>(smem_raw);                       // [2][N][PAD] payload symbols
-  cf *land = ring + 2 * TR::BUF_ELEMS;                               // [2][PAD]    training symbols, one antenna each
-  unsigned char *stage_base = reinterpret_cast<unsigned char *>(land + 2 * PAD);
-  constexpr int stage_stride = 256 * Q;  // 64 carriers x Q LLRs
-  // mbarriers: full[2] (ring slot loaded), yrdy[2] (ring slot transformed), tfull[2] (landing slot loaded),
-  // gdone at 6 (a frame's G is complete), wdone at 7 (the weights of a frame are computed)
-  cf *tw_s = reinterpret_cast<cf *>(stage_base + (size_t)DET_WARPS * 2 * stage_stride);  // stage-1 twiddles, copied once
-  cf *tw2_s = tw_s + TW::CNT1;                                                            // stage 2, k < NT: [(t-1)*NT + k]
-  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(tw2_s + TR::TW2S);
-  unsigned *done = reinterpret_cast<unsigned *>(mbar + 8);           // detect warps done with ring slot [2]
+  cf *land = ring + 2 * TR::BUF_ELEMS;                               // [M]   training symbol as it lands (one antenna)
+  cf *work = land + M;                                               // [PAD] the training symbol being transformed
+  unsigned char *stage_base = reinterpret_cast<unsigned char *>(work + PAD);
+  constexpr int stage_stride = 256 * Q;  // 64 carriers x Q LLRs: one LLR staging slot per detect warp
+  cf *wbuf_base = reinterpret_cast<cf *>(stage_base + (size_t)DET_WARPS * stage_stride);  // [DET_WARPS][WREC] W of the task
+  // mbarriers: full[2] (ring slot loaded), yrdy[2] (ring slot transformed), tfull at 4 (landing row loaded),
+  // gdone at 6 (a frame's G is complete), wdone at 7 (the weights of a frame are computed), wrdy[DET_WARPS] from 8 on
+  // (a detect warp's W record has landed)
+  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(wbuf_base + (size_t)DET_WARPS * TR::WREC);
+  unsigned *done = reinterpret_cast<unsigned *>(mbar + 8 + DET_WARPS);  // detect warps done with ring slot [2]
   volatile unsigned *sched = done + 2;                                // FFT warps: verdict of the work-conserving test
 
   const int tid = threadIdx.x;
@@ -199,15 +211,15 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
   };
   // Training unit number ug of this CTA: frame ug / TU, then (tx t, rx antenna r, code c) with the code fastest,
   // i.e. OFDM symbol c * N + t of antenna r: the nac symbols that accumulate into G[r][t] follow each other.  One
-  // TMA load into landing slot ug & 1.
+  // TMA load into the landing row (free again as soon as the first stage of the previous unit has read it).
   auto issue_training = [&](int ug) {
     const int f = ug / TU, u = ug - f * TU;
     if (f >= nf) return;
     const long long frame = (long long)blockIdx.x + (long long)f * gridDim.x;
     const int c = u % a.nac, r = (u / a.nac) % N, t = u / (a.nac * N);
-    mbar_expect_tx(&mbar[4 + (ug & 1)], sym_bytes);
-    bulk_load(land + (size_t)(ug & 1) * PAD, a.iq + frame * a.frame_stride + a.first_sample + (long long)(c * N + t) * a.L + a.cp +
-              (long long)r * a.rx_stride, sym_bytes, &mbar[4 + (ug & 1)], pol_stream);
+    mbar_expect_tx(&mbar[4], sym_bytes);
+    bulk_load(land, a.iq + frame * a.frame_stride + a.first_sample + (long long)(c * N + t) * a.L + a.cp +
+              (long long)r * a.rx_stride, sym_bytes, &mbar[4], pol_stream);
   };
 
   if (tid == 0) {
@@ -219,17 +231,15 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
     mbar_init(&mbar[5], 1);
     mbar_init(&mbar[6], TR::FFT_WARPS);
     mbar_init(&mbar[7], DET_WARPS);
+    for (int w = 0; w < DET_WARPS; w++) mbar_init(&mbar[8 + w], 1);
     done[0] = 0;
     done[1] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
     issue_training(0);
-    issue_training(1);
     issue_payload(0);
     issue_payload(1);
   }
-  for (int i = tid; i < TW::CNT1; i += TR::THREADS) tw_s[i] = a.tw[TW::OFF1 + i];
-  for (int i = tid; i < TR::TW2S; i += TR::THREADS) tw2_s[i] = a.tw[TW::OFF2 + (i / NT) * TW::NS2 + i % NT];
   __syncthreads();
 
   if (warp < TR::FFT_WARPS) {
@@ -276,11 +286,11 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
         f = ug / TU;
         const int u = ug - f * TU;
         c = u % nac; r0 = (u / nac) % N; t = u / (nac * N);
-        buf = land + (size_t)(ug & 1) * PAD;
+        buf = work;
 
         // the G scratch is free once the weights of the previous frame have been computed from it
         if (u == 0 && f >= 1) mbar_wait(&mbar[7], (unsigned)((f - 1) & 1));
-        mbar_wait(&mbar[4 + (ug & 1)], (unsigned)((ug >> 1) & 1));
+        mbar_wait(&mbar[4], (unsigned)(ug & 1));
       } else {
         f = pg / D;
         buf = ring + (size_t)(pg & 1) * TR::BUF_ELEMS;
@@ -290,19 +300,28 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
       unsigned sgb[B2];
 #pragma unroll
       for (int b = 0; b < B2; b++) sgb[b] = training ? (unsigned)fa.sgn8[((size_t)t * nac + c) * (M / R2) + ft + b * NT] : 0u;
-      // In place, stage by stage over the job's antennas; the twiddles of a stage depend on the thread only
-      // and are read once per job.  The barrier between a pair's loads and its stores also orders the stores
-      // of the previous pair before the next stage's loads of that antenna (N >= 2 pairs later); a one-antenna
-      // job needs a barrier of its own between the stages.
+      // In place, stage by stage over the job's antennas (a training unit: from the landing row into the work row);
+      // the twiddles of a stage depend on the thread only and are read once per job.  The barrier between an
+      // antenna's loads and its stores also orders the stores of the previous antenna before the next stage's
+      // loads of it (N antennas later); a one-antenna job needs a barrier of its own between the stages.  The
+      // barriers sit AFTER the butterflies: a barrier only orders the issue of loads, and a load still queued in
+      // another scheduler's LSU pipe can be overtaken by the async proxy (the TMA refill of the landing row);
+      // having consumed the loaded values, every thread's loads have been performed when it arrives.
+#if (RUB_WS_ABLATE & 1)  // measurement only: no transform at all (results are wrong)
+#pragma unroll
+      for (int i = 0; i < FF::PTS; i++) v[i] = mk(0.f, 0.f);
+      if (training) { named_bar(1, NT); if (tid == 0) issue_training(ug + 1); }
+#else
 #pragma unroll 1
       for (int r = 0; r < nr; r++) {
         cf *reg = buf + (size_t)r * PAD;
-        FF::S0::template load<false>(ft, reg, v);
-        named_bar(1, NT);
+        FF::S0::template load<false>(ft, training ? land : reg, v);
         FF::S0::compute(ft, v, nullptr);
+        named_bar(1, NT);
+        if (training && tid == 0) issue_training(ug + 1);
         FF::S0::template store<true, false>(ft, v, reg, 1.f);
       }
-      FF::S1::load_twiddles(ft, tw_s, tw);
+      FF::S1::load_twiddles(ft, a.tw + TW::OFF1, tw);
       if (training) named_bar(1, NT);
 #pragma unroll 1
       for (int r = 0; r < nr; r++) {
@@ -310,30 +329,28 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
         FF::S1::template load<true>(ft, reg, v);
         named_bar(1, NT);
         FF::S1::compute_pre(v, tw);
-        FF::S1::template store<true, false>(ft, v, reg, 1.f);
+        // unpadded: NS1 consecutive lanes write consecutive elements (conflict free without the pad), and the last
+        // stage then reads and writes the same M/R2-strided positions per butterfly, i.e. it is in place per thread
+        FF::S1::template store<false, false>(ft, v, reg, 1.f);
       }
-      // last-stage twiddles: tw[b * (R2 - 1) + t - 1] = table[(t - 1) * NS2 + ft + b * NT]; butterfly 0 from shared
-      // memory, the others from global memory
+      // last-stage twiddles: tw[b * (R2 - 1) + t - 1] = table[(t - 1) * NS2 + ft + b * NT] (global memory / L1: shared
+      // memory is spent on the rings and the W records)
 #pragma unroll
       for (int b = 0; b < B2; b++)
 #pragma unroll
         for (int t2 = 1; t2 < R2; t2++)
-          tw[b * (R2 - 1) + t2 - 1] = (b == 0) ? tw2_s[(t2 - 1) * NT + ft] : a.tw[TW::OFF2 + (t2 - 1) * NS2 + (ft + b * NT) % NS2];
-      if (training) named_bar(1, NT);
+          tw[b * (R2 - 1) + t2 - 1] = ld_tw(a.tw + TW::OFF2 + (t2 - 1) * NS2 + (ft + b * NT) % NS2);
+      named_bar(1, NT);  // the stage-1 stores of the last antenna are visible
 #pragma unroll 1
       for (int r = 0; r < nr; r++) {
         cf *reg = buf + (size_t)r * PAD;
-        FF::S2::template load<true>(ft, reg, v);
+        FF::S2::template load<false>(ft, reg, v);
         FF::S2::compute_pre(v, tw);
-        // The barrier orders every thread's loads of the region before any store into it (payload: the in-place
-        // stores below; training: the TMA refill of the landing slot).  It sits AFTER the butterflies on purpose:
-        // a barrier only orders the issue of loads, and a load still queued in another scheduler's LSU pipe
-        // can be overtaken by the async proxy; having consumed the loaded values, every thread's loads have been
-        // performed when it arrives.
-        named_bar(1, NT);
-        if (training && tid == 0) issue_training(ug + 2);
+        // payload: in place per butterfly, no barrier; training: the outputs stay in registers (the work row is
+        // rewritten by the next unit's first stage behind that stage's barrier)
         if (!training) FF::S2::template store<false, true>(ft, v, reg, a.dn);
       }
+#endif
       if (!training) {
         // Y complete: every lane's stores are ordered before lane 0's release-arrive
         __syncwarp();
@@ -366,7 +383,13 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
 #pragma unroll
             for (int t2 = 0; t2 < R2; t2++) {
               const int j = ft + b * NT, k = (j / NS2) * NS2 * R2 + (j % NS2) + t2 * NS2;
+#if RUB_WS_GPOL == 0
               st_hint2(Gf + k, acc[b * R2 + t2], pol_stream);
+#elif RUB_WS_GPOL == 1
+              *reinterpret_cast<float2 *>(Gf + k) = acc[b * R2 + t2];
+#else
+              st_hint2(Gf + k, acc[b * R2 + t2], pol_keep);
+#endif
             }
         }
         ug++;
@@ -390,7 +413,11 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
   for (int i = 0; i < 4; i++) refs[i] = (i < MB) ? (float)(1u << (MB - 1 - i)) * dc.alpha : 0.f;
   const int koff = dwarp * 64 + 2 * lane;                // first carrier of this lane in block kb = 0
   constexpr int KSTEP = 64 * DET_WARPS;                  // carrier distance between a warp's blocks
-  unsigned char *slot0 = stage_base + (size_t)(dwarp * 2) * stage_stride;  // this warp's two LLR staging slots
+  unsigned char *slot = stage_base + (size_t)dwarp * stage_stride;  // this warp's LLR staging slot
+  cf *wbuf = wbuf_base + (size_t)dwarp * TR::WREC;                  // this warp's W record (TMA destination)
+  unsigned long long *wrdy = &mbar[8 + dwarp];
+  constexpr int KB = M / 64;                                         // 64-carrier blocks per symbol
+  unsigned wn = 0;                                                   // W records consumed so far (mbarrier phase)
   // per-lane error counts, 16 bits per stream (streams 0,1 in word 0; 2,3 in word 1)
   unsigned eb0 = 0, eb1 = 0, es0 = 0, es1 = 0;
   // the 16-bit fields must survive the warp sum: flush before 32 lanes x bit errors can reach 65536
@@ -416,7 +443,7 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
     const cf *Gc = fa.scratchAcc + (size_t)blockIdx.x * N * N * M;
     float *gc = fa.scratchG + (size_t)blockIdx.x * 2 * N * M, *ic = gc + (size_t)N * M;
     // ---------------- weights (mimo/framing.cc:817-832) ----------------
-    mbar_wait(&mbar[6], (unsigned)(f & 1));  // G(f) is complete (written by the FFT warps)
+    mbar_wait_backoff(&mbar[6], (unsigned)(f & 1), RUB_WS_BACKOFF_NS);  // G(f) is complete (written by the FFT warps)
     if (f > 0) named_bar(2, DET_THREADS);     // every detect warp is done reading the previous frame's W
 #pragma unroll 1
     for (int k = dtid; k < M; k += DET_THREADS) {
@@ -432,22 +459,32 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
         for (int e = 0; e < N * N; e++) a.G[(frame * N * N + e) * M + k] = G[e];
       }
       compute_weights<N>(fa.wm, G, W, gain, isig);
+      // W in task records: [stream][64-carrier block][rx][64], one 64*N*8-byte bulk copy per detection task
 #pragma unroll
-      for (int e = 0; e < N * N; e++) st_hint2(Wc + (size_t)e * M + k, make_float2(W[e].x, W[e].y), pol_keep);
+      for (int e = 0; e < N * N; e++)
+        st_hint2(Wc + ((size_t)((e / N) * KB + (k >> 6)) * N + (e % N)) * 64 + (k & 63), make_float2(W[e].x, W[e].y), pol_keep);
 #pragma unroll
       for (int s = 0; s < N; s++) { st_hint1(gc + (size_t)s * M + k, gain[s], pol_keep); st_hint1(ic + (size_t)s * M + k, isig[s], pol_keep); }
     }
+    // the W records are read through the async proxy (TMA): order this thread's generic-proxy stores before it
+    __threadfence();
+    asm volatile("fence.proxy.async;" ::: "memory");
     // the G scratch has been consumed: the FFT warps may start on the frame after this one
     __syncwarp();
     if (lane == 0) mbar_arrive(&mbar[7]);
     named_bar(2, DET_THREADS);  // W complete before any warp reads it; every warp is past the previous frame
+    // W record of detection task (stream s, block kb of this warp) -> this warp's buffer (one lane)
+    auto issue_w = [&](int s_, int kb_) {
+      mbar_expect_tx(wrdy, (unsigned)(TR::WREC * sizeof(cf)));
+      bulk_load(wbuf, Wc + ((size_t)(s_ * KB + dwarp + kb_ * DET_WARPS) * N) * 64, (unsigned)(TR::WREC * sizeof(cf)), wrdy, pol_keep);
+    };
+    if (lane == 0) issue_w(0, 0);
 
     // ---------------- detect + demap + count, payload symbol by payload symbol ----------------
 #pragma unroll 1
     for (int d = 0; d < D; d++, pg++) {
       const int b = pg & 1;
       const cf *buf = ring + (size_t)b * TR::BUF_ELEMS;
-      const cf *wp = Wc + koff;         // W[s][0][k] of the current task (this lane's carriers)
       const float *gp = gc + koff;      // gain[s][k]; isig follows N*M floats later
       long long o = (frame * N * D + d) * (long long)M + koff;  // output index: stream 0, block 0, this lane
       const long long DM = (long long)D * M;
@@ -457,22 +494,22 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
       const long long bo_s = DM / 8 * Q, bo_k = (long long)KSTEP / 8 * Q - (N - 1) * bo_s;
       TaskRegs<N> w;
       unsigned txv = 0;  // transmitted symbols of the two carriers of the task
-      auto load_w = [&]() {
-#pragma unroll
-        for (int r = 0; r < N; r++) w.w[r] = ld_hint4(wp + r * M, pol_keep);
+      auto load_w = [&]() {  // gain, 1/sigma^2 and the reference symbols of the next task (W itself comes by TMA)
         w.g = ld_hint2(gp, pol_keep);
         w.is = ld_hint2(gp + N * M, pol_keep);
+#if !RUB_WS_NOTX
         if (a.tx_data) txv = ld_hint_u16(a.tx_data + o, pol_stream);
+#endif
       };
       load_w();  // first task: requested before Y is needed
       if (a.tx_data && lane < KPW * N) {
         // the reference symbols of this warp's tasks of the NEXT payload symbol: pull their lines into L2 now so
-        // that the 2-byte loads riding with the W loads never wait for HBM
+        // that the 2-byte loads riding with the gain loads never wait for HBM
         const unsigned char *tp = a.tx_data + (o - 2 * lane) + (long long)(lane % N) * DM + (lane / N) * KSTEP;
         if (d == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(tp));
         if (d + 1 < D) asm volatile("prefetch.global.L2 [%0];" ::"l"(tp + M));
       }
-      mbar_wait(&mbar[2 + b], (unsigned)((pg >> 1) & 1));
+      mbar_wait_backoff(&mbar[2 + b], (unsigned)((pg >> 1) & 1), RUB_WS_BACKOFF_NS);
       int it = 0;
 #pragma unroll 1
       for (int kb = 0; kb < KPW; kb++) {
@@ -489,23 +526,39 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
             issue_payload(pg + 2);
           }
         }
+#if (RUB_WS_ABLATE & 2)  // measurement only: no detection (results are wrong)
+        if (y4[0].x == 123.456f) eb0++;
+        continue;
+#endif
 #pragma unroll 1
         for (int s = 0; s < N; s++, it++) {
           cf z0, z1;
           const float2 is = w.is;
           const unsigned tx2 = txv;
           const long long oc = o, boc = bo;
+          mbar_wait(wrdy, wn & 1u);
+          wn++;
+#pragma unroll
+          for (int r = 0; r < N; r++) w.w[r] = *reinterpret_cast<const float4 *>(wbuf + r * 64 + 2 * lane);
           ws_dot<N>(w, y4, z0, z1);
+          // The record of the next task of this frame (the next symbol starts over at task 0).  The proxy fence
+          // waits for this lane's loads of the buffer (their values went into the products above) before the
+          // copy may overwrite it.
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (it + 1 < KPW * N) issue_w(s + 1 < N ? s + 1 : 0, s + 1 < N ? kb : kb + 1);
+            else if (d + 1 < D) issue_w(0, 0);
+          }
           const unsigned rx2 = ws_hard<MB>(a, refs, z0, z1, oc, reinterpret_cast<unsigned short *>(a.bits + boc + (lane >> 2) * Q),
                                            pol_stream, lane);
-          // W of the next task lands in the registers the products released
-          if (s + 1 < N) { wp += N * M; gp += M; o += DM; bo += bo_s; }
-          else { wp += KSTEP - (N - 1) * N * M; gp += KSTEP - (N - 1) * M; o += (long long)KSTEP - (N - 1) * DM; bo += bo_k; }
+          // gain / isig / tx of the next task land in the registers the products released
+          if (s + 1 < N) { gp += M; o += DM; bo += bo_s; }
+          else { gp += KSTEP - (N - 1) * M; o += (long long)KSTEP - (N - 1) * DM; bo += bo_k; }
           if (it + 1 < KPW * N) load_w();
           if (a.llr) {
-            unsigned char *slot = slot0 + (it & 1) * stage_stride;
-            // the bulk store issued two tasks ago from this staging slot must have drained
-            if (lane == 0) bulk_wait_read<1>();
+            // the bulk store of the previous task must have read the staging slot
+            if (lane == 0) bulk_wait_read<0>();
             __syncwarp();
             ws_llr<MB>(dc, z0, z1, is, reinterpret_cast<float *>(slot) + lane * 2 * Q);
             fence_async_smem();
