@@ -159,6 +159,102 @@ __global__ void k_weights(ChainArgs a, WeightMode wm) {
   for (int s = 0; s < N; s++) { gf[(long long)s * a.M + k] = gain[s]; sf[(long long)s * a.M + k] = isig[s]; }
 }
 
+// ---- K2+K3 for the comb estimator in one pass: G never goes to HBM (it is written only when the caller asked
+// for it).  CTA = 128 consecutive carriers of one frame: the pilots that bracket them (128 / P + 2 per antenna
+// pair) are evaluated once into shared memory with comb_pilot(), every thread then interpolates its carrier's N*N
+// entries with the expressions of k_ls_comb (bit-identical) and goes on with compute_weights<N>.
+template <int N>
+__global__ void __launch_bounds__(128) k_lscomb_weights(ChainArgs a, WeightMode wm, int write_G) {
+  constexpr int TPB = 128, U = 3;
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  cf *pil = reinterpret_cast<cf *>(sm_raw);  // [N*N][J]
+  const int P = a.P, lp = 31 - __clz(P), np = a.M >> lp, J = (TPB >> lp) + 2;  // P | M and M = 2^m: P is a power of two
+  const int tiles = (a.M + TPB - 1) / TPB;
+  const int frame = blockIdx.x / tiles, kt0 = (blockIdx.x % tiles) * TPB;
+  const int E = N * N * J;
+  const float invJ = 1.0f / (float)J;
+  const long long nsym = a.T + a.D;
+  const bool q1 = (a.flags & RUB_FLAG_Q1_IDENTITY_INIT) != 0;
+  // pilots of the tile, U entries per thread at a time so that their loads are in flight together; the sums are
+  // comb_pilot()'s, in its order
+  for (int e0 = threadIdx.x; e0 < E; e0 += U * TPB) {
+    int r[U], t[U], kp[U];
+    bool ok[U];
+    cf acc[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int e = e0 + u * TPB;
+      int pair = (int)(((float)e + 0.5f) * invJ);
+      if (pair * J > e) pair--;            // guard the float quotient
+      if ((pair + 1) * J <= e) pair++;
+      const int j = e - pair * J;
+      r[u] = pair / N; t[u] = pair - r[u] * N;
+      const int i = (kt0 >= t[u] ? (kt0 - t[u]) >> lp : 0) + j;
+      kp[u] = t[u] + (i << lp);
+      ok[u] = e < E && i < np;
+      acc[u] = mk((q1 && r[u] == t[u]) ? 1.0f : 0.0f, 0.f);
+    }
+    for (int c = 0; c < a.nac; c++) {
+      cf X[U];
+      float sg[U];
+#pragma unroll
+      for (int u = 0; u < U; u++)
+        if (ok[u]) {
+          X[u] = a.Y[(((long long)frame * nsym + c) * a.N + r[u]) * a.M + kp[u]];
+          sg[u] = a.sgn[((long long)t[u] * a.nac + c) * a.M + kp[u]];
+        }
+#pragma unroll
+      for (int u = 0; u < U; u++)
+        if (ok[u]) { acc[u].x = acc[u].x + X[u].x * sg[u]; acc[u].y = acc[u].y + X[u].y * sg[u]; }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++)
+      if (ok[u]) pil[e0 + u * TPB] = cscale(acc[u], a.s_ls);
+  }
+  __syncthreads();
+  const int k = kt0 + threadIdx.x;
+  if (k >= a.M) return;
+  cf *Wf = a.W + (long long)frame * N * N * a.M;
+  float *gf = a.gain + (long long)frame * N * a.M, *sf = a.isig + (long long)frame * N * a.M;
+  cf G[N * N], W[N * N];
+  float gain[N], isig[N];
+  const float invP = 1.0f / (float)P;
+#pragma unroll
+  for (int t = 0; t < N; t++) {
+    // position of carrier k in tx t's comb: the same for every rx antenna
+    const int kt = k - t;
+    const bool below = kt < 0;                                  // hold below the first pilot
+    const int i = below ? 0 : kt >> lp, d = below ? 0 : kt & (P - 1);
+    const int j = i - (kt0 >= t ? (kt0 - t) >> lp : 0);
+    const bool hold = d == 0 || i + 1 >= np;                    // a pilot itself, or held above the last one
+    const float f = (float)d * invP;
+#pragma unroll
+    for (int r = 0; r < N; r++) {
+      const cf *pp = pil + (r * N + t) * J + j;
+      const cf ga = pp[0], gb = pp[1];                          // gb is unused (possibly unwritten) when hold
+      const cf gi = mk(fmaf(f, gb.x - ga.x, ga.x), fmaf(f, gb.y - ga.y, ga.y));
+      G[r * N + t] = hold ? ga : gi;
+    }
+  }
+  if (write_G) {
+    cf *Gf = a.G + (long long)frame * N * N * a.M;
+#pragma unroll
+    for (int e = 0; e < N * N; e++) Gf[(long long)e * a.M + k] = G[e];
+  }
+  if (a.scnull[k]) {
+#pragma unroll
+    for (int e = 0; e < N * N; e++) Wf[(long long)e * a.M + k] = mk(0.f, 0.f);
+#pragma unroll
+    for (int s = 0; s < N; s++) { gf[(long long)s * a.M + k] = 0.f; sf[(long long)s * a.M + k] = 0.f; }
+    return;
+  }
+  compute_weights<N>(wm, G, W, gain, isig);
+#pragma unroll
+  for (int e = 0; e < N * N; e++) Wf[(long long)e * a.M + k] = W[e];
+#pragma unroll
+  for (int s = 0; s < N; s++) { gf[(long long)s * a.M + k] = gain[s]; sf[(long long)s * a.M + k] = isig[s]; }
+}
+
 // ---- K4: detect + demap + count (mimo/framing.cc:569-586, mimo/main.cc:1403-1410) --------
 // blockIdx.x = (frame, symbol, stream); each thread owns 8 consecutive occupied carriers so
 // its packed hard bits are whole bytes for every modulation.

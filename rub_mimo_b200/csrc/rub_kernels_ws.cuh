@@ -30,13 +30,8 @@
 #include "rub_kernels_fused.cuh"
 
 #ifndef RUB_WS_ABLATE
-#define RUB_WS_ABLATE 0  // 1: FFT warps skip the transform, 2: detect warps skip detection (tools/dev only)
-#endif
-#ifndef RUB_WS_NOTX
-#define RUB_WS_NOTX 0  // measurement only: no tx_data loads (wrong counters)
-#endif
-#ifndef RUB_WS_GPOL
-#define RUB_WS_GPOL 0
+#define RUB_WS_ABLATE 0  // measurement builds only (wrong results): 1 FFT warps skip the transform, 2 detect warps skip
+                         // detection, 4 no G scratch stores, 8 no W/gain/isig scratch stores
 #endif
 #ifndef RUB_WS_BACKOFF_NS
 #define RUB_WS_BACKOFF_NS 100
@@ -121,19 +116,19 @@ __device__ __forceinline__ void ws_dot(const TaskRegs<N> &t, const float4 *y4, c
 // hard decisions of the task: equalised symbols out, slicer, packed bits; returns the two demodulated symbols
 // (sym0 | sym1 << 8).  Runs BEFORE the next task's W loads are requested: its warp shuffles must not share a
 // scoreboard with loads that take an L2 round trip.
-template <int MB>
-__device__ __forceinline__ unsigned ws_hard(const ChainArgs &a, const float *refs, cf z0, cf z1, long long o,
+template <int MB, bool FULL>
+__device__ __forceinline__ unsigned ws_hard(const float *refs, cf z0, cf z1, cf *eqp, unsigned char *rxp,
                                             unsigned short *bp, unsigned long long pol_stream, int lane) {
   constexpr int Q = 2 * MB;
-  if (a.eq) st_hint4(a.eq + o, make_float4(z0.x, z0.y, z1.x, z1.y), pol_stream);
+  if (FULL || eqp) st_hint4(eqp, make_float4(z0.x, z0.y, z1.x, z1.y), pol_stream);
   const unsigned si0 = slice_axis_refs<MB>(z0.x, refs), sq0 = slice_axis_refs<MB>(z0.y, refs);
   const unsigned si1 = slice_axis_refs<MB>(z1.x, refs), sq1 = slice_axis_refs<MB>(z1.y, refs);
   // (gray(si) << MB) | gray(sq) in one pass: the bit shifted from si into sq's top position is masked off
   const unsigned c0 = (si0 << MB) | sq0, c1 = (si1 << MB) | sq1;
   const unsigned sym0 = c0 ^ ((c0 >> 1) & ~(1u << (MB - 1))), sym1 = c1 ^ ((c1 >> 1) & ~(1u << (MB - 1)));
   const unsigned rx2 = sym0 | (sym1 << 8);
-  if (a.rx_data) *reinterpret_cast<unsigned short *>(a.rx_data + o) = (unsigned short)rx2;
-  if (a.bits) {
+  if (!FULL && rxp) *reinterpret_cast<unsigned short *>(rxp) = (unsigned short)rx2;
+  if (FULL || bp) {
     // 4 lanes = 8 symbols = Q bytes, MSB first, written by the first lane of each quad
     const unsigned v2 = (sym0 << Q) | sym1;                                   // 2Q bits
     const unsigned p1 = __shfl_xor_sync(0xffffffffu, v2, 1);
@@ -165,7 +160,9 @@ __device__ __forceinline__ void ws_llr(const DemapConst &dc, cf z0, cf z1, float
     *reinterpret_cast<float4 *>(lp + 4 * v) = make_float4(l[4 * v], l[4 * v + 1], l[4 * v + 2], l[4 * v + 3]);
 }
 
-template <int LOG2M, int N, int MB>
+// FULL: the caller asked for eq + LLR + bits + counters and no rx_data (the usual set): the per-task null checks
+// of the output pointers are compiled out
+template <int LOG2M, int N, int MB, bool FULL>
 __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedArgs fa, DemapConst dc) {
   using TR = WsTraits<LOG2M, N>;
   using FF = Fft<LOG2M>;
@@ -376,20 +373,14 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
             acc[i] = ac;
           }
         }
-        if (c == nac - 1) {
+        if (c == nac - 1 && !(RUB_WS_ABLATE & 4)) {
           cf *Gf = fa.scratchAcc + (size_t)blockIdx.x * N * N * M + (size_t)(r0 * N + t) * M;
 #pragma unroll
           for (int b = 0; b < B2; b++)
 #pragma unroll
             for (int t2 = 0; t2 < R2; t2++) {
               const int j = ft + b * NT, k = (j / NS2) * NS2 * R2 + (j % NS2) + t2 * NS2;
-#if RUB_WS_GPOL == 0
               st_hint2(Gf + k, acc[b * R2 + t2], pol_stream);
-#elif RUB_WS_GPOL == 1
-              *reinterpret_cast<float2 *>(Gf + k) = acc[b * R2 + t2];
-#else
-              st_hint2(Gf + k, acc[b * R2 + t2], pol_keep);
-#endif
             }
         }
         ug++;
@@ -442,6 +433,14 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
     cf *Wc = fa.scratchW + (size_t)blockIdx.x * N * N * M;
     const cf *Gc = fa.scratchAcc + (size_t)blockIdx.x * N * N * M;
     float *gc = fa.scratchG + (size_t)blockIdx.x * 2 * N * M, *ic = gc + (size_t)N * M;
+    // this frame's outputs; inside a frame 32-bit element offsets do ((stream * D + symbol) * M + carrier)
+    const long long fbase = frame * N * (long long)D * M;
+    cf *const eqf = (FULL || a.eq) ? a.eq + fbase : nullptr;
+    unsigned char *const rxf = (!FULL && a.rx_data) ? a.rx_data + fbase : nullptr;
+    unsigned char *const bitsf = (FULL || a.bits) ? a.bits + fbase / 8 * Q : nullptr;
+    unsigned char *const llrf = (FULL || a.llr) ? reinterpret_cast<unsigned char *>(a.llr) + fbase * (Q * 4) : nullptr;
+    const unsigned char *const txf = (FULL || a.tx_data) ? a.tx_data + fbase : nullptr;
+    const int DMi = D * M;
     // ---------------- weights (mimo/framing.cc:817-832) ----------------
     mbar_wait_backoff(&mbar[6], (unsigned)(f & 1), RUB_WS_BACKOFF_NS);  // G(f) is complete (written by the FFT warps)
     if (f > 0) named_bar(2, DET_THREADS);     // every detect warp is done reading the previous frame's W
@@ -460,9 +459,15 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
       }
       compute_weights<N>(fa.wm, G, W, gain, isig);
       // W in task records: [stream][64-carrier block][rx][64], one 64*N*8-byte bulk copy per detection task
+#if (RUB_WS_ABLATE & 8)  // measurement only: no scratch stores
+      if (k < 0)
+#endif
 #pragma unroll
       for (int e = 0; e < N * N; e++)
         st_hint2(Wc + ((size_t)((e / N) * KB + (k >> 6)) * N + (e % N)) * 64 + (k & 63), make_float2(W[e].x, W[e].y), pol_keep);
+#if (RUB_WS_ABLATE & 8)
+      if (k < 0)
+#endif
 #pragma unroll
       for (int s = 0; s < N; s++) { st_hint1(gc + (size_t)s * M + k, gain[s], pol_keep); st_hint1(ic + (size_t)s * M + k, isig[s], pol_keep); }
     }
@@ -485,27 +490,29 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
     for (int d = 0; d < D; d++, pg++) {
       const int b = pg & 1;
       const cf *buf = ring + (size_t)b * TR::BUF_ELEMS;
-      const float *gp = gc + koff;      // gain[s][k]; isig follows N*M floats later
-      long long o = (frame * N * D + d) * (long long)M + koff;  // output index: stream 0, block 0, this lane
-      const long long DM = (long long)D * M;
-      // byte offset of the task's 64-carrier block in the packed-bits output (Q bytes per 8 carriers); the
-      // block's LLRs start 32 times as far into the LLR output
-      long long bo = ((frame * N * D + d) * (long long)M + dwarp * 64) / 8 * Q;
-      const long long bo_s = DM / 8 * Q, bo_k = (long long)KSTEP / 8 * Q - (N - 1) * bo_s;
-      TaskRegs<N> w;
-      unsigned txv = 0;  // transmitted symbols of the two carriers of the task
+      int gi = koff;                    // gain[s][k] index of the task; isig follows N*M floats later
+      int ob = 0;                       // element offset of the task's block from the symbol's (stream 0, block 0)
+      // this symbol's output positions of the lane / the warp's block, kept in registers (the compiler would
+      // otherwise rebuild them from the kernel arguments in every task)
+      const int d0 = d * M + dwarp * 64;
+      cf *eqd = eqf + d0 + 2 * lane;
+      const unsigned char *txd = txf + d0 + 2 * lane;
+      unsigned char *rxd = rxf ? rxf + d0 + 2 * lane : nullptr;
+      unsigned char *bitd = bitsf + ((d0 >> 3) + (lane >> 2)) * Q;
+      unsigned char *llrd = llrf + (size_t)d0 * (Q * 4);
+      asm volatile("" : "+l"(eqd), "+l"(txd), "+l"(bitd), "+l"(llrd));
+      float2 tg, tis;                   // gain, 1/sigma_eff^2 of the lane's two carriers
+      unsigned txv = 0;                 // transmitted symbols of the two carriers of the task
       auto load_w = [&]() {  // gain, 1/sigma^2 and the reference symbols of the next task (W itself comes by TMA)
-        w.g = ld_hint2(gp, pol_keep);
-        w.is = ld_hint2(gp + N * M, pol_keep);
-#if !RUB_WS_NOTX
-        if (a.tx_data) txv = ld_hint_u16(a.tx_data + o, pol_stream);
-#endif
+        tg = ld_hint2(gc + gi, pol_keep);
+        tis = ld_hint2(gc + gi + N * M, pol_keep);
+        if (FULL || txf) txv = ld_hint_u16(txd + ob, pol_stream);
       };
       load_w();  // first task: requested before Y is needed
-      if (a.tx_data && lane < KPW * N) {
+      if ((FULL || txf) && lane < KPW * N) {
         // the reference symbols of this warp's tasks of the NEXT payload symbol: pull their lines into L2 now so
         // that the 2-byte loads riding with the gain loads never wait for HBM
-        const unsigned char *tp = a.tx_data + (o - 2 * lane) + (long long)(lane % N) * DM + (lane / N) * KSTEP;
+        const unsigned char *tp = txf + d0 + (lane % N) * DMi + (lane / N) * KSTEP;
         if (d == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(tp));
         if (d + 1 < D) asm volatile("prefetch.global.L2 [%0];" ::"l"(tp + M));
       }
@@ -533,9 +540,11 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
 #pragma unroll 1
         for (int s = 0; s < N; s++, it++) {
           cf z0, z1;
-          const float2 is = w.is;
+          TaskRegs<N> w;
+          w.g = tg;
+          const float2 is = tis;
           const unsigned tx2 = txv;
-          const long long oc = o, boc = bo;
+          const int obc = ob;
           mbar_wait(wrdy, wn & 1u);
           wn++;
 #pragma unroll
@@ -550,13 +559,14 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
             if (it + 1 < KPW * N) issue_w(s + 1 < N ? s + 1 : 0, s + 1 < N ? kb : kb + 1);
             else if (d + 1 < D) issue_w(0, 0);
           }
-          const unsigned rx2 = ws_hard<MB>(a, refs, z0, z1, oc, reinterpret_cast<unsigned short *>(a.bits + boc + (lane >> 2) * Q),
-                                           pol_stream, lane);
+          const unsigned rx2 = ws_hard<MB, FULL>(refs, z0, z1, (FULL || eqf) ? eqd + obc : nullptr, rxd ? rxd + obc : nullptr,
+                                                 (FULL || bitsf) ? reinterpret_cast<unsigned short *>(bitd + (obc >> 3) * Q) : nullptr,
+                                                 pol_stream, lane);
           // gain / isig / tx of the next task land in the registers the products released
-          if (s + 1 < N) { gp += M; o += DM; bo += bo_s; }
-          else { gp += KSTEP - (N - 1) * M; o += (long long)KSTEP - (N - 1) * DM; bo += bo_k; }
+          if (s + 1 < N) { gi += M; ob += DMi; }
+          else { gi += KSTEP - (N - 1) * M; ob += KSTEP - (N - 1) * DMi; }
           if (it + 1 < KPW * N) load_w();
-          if (a.llr) {
+          if (FULL || llrf) {
             // the bulk store of the previous task must have read the staging slot
             if (lane == 0) bulk_wait_read<0>();
             __syncwarp();
@@ -564,11 +574,11 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
             fence_async_smem();
             __syncwarp();
             if (lane == 0) {
-              bulk_store(reinterpret_cast<unsigned char *>(a.llr) + boc * 32, slot, (unsigned)(64 * Q * 4), pol_stream);
+              bulk_store(llrd + obc * (Q * 4), slot, (unsigned)(64 * Q * 4), pol_stream);
               bulk_commit();
             }
           }
-          if (a.tx_data) {
+          if (FULL || txf) {
             const unsigned x = rx2 ^ tx2;
             const unsigned vb = (unsigned)__popc(x) << (16 * (s & 1));
             const unsigned vs = (((x & 0xffu) != 0u ? 1u : 0u) + ((x >> 8) != 0u ? 1u : 0u)) << (16 * (s & 1));
@@ -576,7 +586,7 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
           }
         }
       }
-      if (a.tx_data && (++since_flush == flush_every || d == D - 1)) { flush_counts(since_flush); since_flush = 0; }
+      if ((FULL || a.tx_data) && (++since_flush == flush_every || d == D - 1)) { flush_counts(since_flush); since_flush = 0; }
     }
   }
   if (lane == 0) bulk_wait_all();

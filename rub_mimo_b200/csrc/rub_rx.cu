@@ -347,9 +347,16 @@ static void launch_fft(const ChainArgs &a, cudaStream_t st, cudaError_t *err) {
   k_fft_staged<LOG2M, F><<<grid, NT * F, smem, st>>>(a);
 }
 template <int N>
-static void launch_weights_detect(const ChainArgs &a, const rub_rx *h, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1) {
+static void launch_weights_detect(const ChainArgs &a, const rub_rx *h, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1,
+                                  int comb_fused, int write_G) {
   const long long tw = (long long)a.n_frames * a.M;
-  k_weights<N><<<(unsigned)((tw + 127) / 128), 128, 0, st>>>(a, h->wm);
+  if (comb_fused) {
+    // comb LS + weights in one kernel (the pilots of a 128-carrier tile in shared memory)
+    const size_t sm = (size_t)N * N * (128 / a.P + 2) * sizeof(cf);
+    k_lscomb_weights<N><<<(unsigned)(a.n_frames * ((a.M + 127) / 128)), 128, sm, st>>>(a, h->wm, write_G);
+  } else {
+    k_weights<N><<<(unsigned)((tw + 127) / 128), 128, 0, st>>>(a, h->wm);
+  }
   if (e0) cudaEventRecord(e0, st);
   if (detect_lean_launch(a, h->lut, st)) {
     if (e1) cudaEventRecord(e1, st);
@@ -414,7 +421,11 @@ static rub_status run_staged(rub_rx *h, ChainArgs a, const rub_rx_io *io, uint32
     }
     CUDA_TRY(ferr);
     const long long tg = (long long)nf * c.N * c.N * c.M;
-    if (c.c.estimator == RUB_EST_LS_COMB_INTERP) {
+    // comb estimator: LS and weights share one kernel unless the pilot spacing is so tight that a tile's pilots
+    // do not fit the static bound of its shared-memory table (P < N never happens for a valid comb)
+    const int comb_fused = c.c.estimator == RUB_EST_LS_COMB_INTERP && c.P >= c.N && c.P <= 128;
+    if (comb_fused) {
+    } else if (c.c.estimator == RUB_EST_LS_COMB_INTERP) {
       const long long tp = tg / c.P;  // one thread per pilot
       k_ls_comb<<<(unsigned)((tp + 255) / 256), 256, 0, h->stream>>>(b);
     }
@@ -422,14 +433,14 @@ static rub_status run_staged(rub_rx *h, ChainArgs a, const rub_rx_io *io, uint32
     const bool last = f0 + nf >= n_frames;
     cudaEvent_t e0 = (timed && last) ? h->ev[2] : nullptr, e1 = (timed && last) ? h->ev[3] : nullptr;
     switch (c.N) {
-      case 1: launch_weights_detect<1>(b, h, h->stream, e0, e1); break;
-      case 2: launch_weights_detect<2>(b, h, h->stream, e0, e1); break;
-      case 3: launch_weights_detect<3>(b, h, h->stream, e0, e1); break;
-      case 4: launch_weights_detect<4>(b, h, h->stream, e0, e1); break;
-      case 5: launch_weights_detect<5>(b, h, h->stream, e0, e1); break;
-      case 6: launch_weights_detect<6>(b, h, h->stream, e0, e1); break;
-      case 7: launch_weights_detect<7>(b, h, h->stream, e0, e1); break;
-      case 8: launch_weights_detect<8>(b, h, h->stream, e0, e1); break;
+      case 1: launch_weights_detect<1>(b, h, h->stream, e0, e1, comb_fused, user_G ? 1 : 0); break;
+      case 2: launch_weights_detect<2>(b, h, h->stream, e0, e1, comb_fused, user_G ? 1 : 0); break;
+      case 3: launch_weights_detect<3>(b, h, h->stream, e0, e1, comb_fused, user_G ? 1 : 0); break;
+      case 4: launch_weights_detect<4>(b, h, h->stream, e0, e1, comb_fused, user_G ? 1 : 0); break;
+      case 5: launch_weights_detect<5>(b, h, h->stream, e0, e1, comb_fused, user_G ? 1 : 0); break;
+      case 6: launch_weights_detect<6>(b, h, h->stream, e0, e1, comb_fused, user_G ? 1 : 0); break;
+      case 7: launch_weights_detect<7>(b, h, h->stream, e0, e1, comb_fused, user_G ? 1 : 0); break;
+      case 8: launch_weights_detect<8>(b, h, h->stream, e0, e1, comb_fused, user_G ? 1 : 0); break;
     }
     h->launches += 4;
     CUDA_TRY(cudaGetLastError());

@@ -16,10 +16,12 @@ template <int LOG2M, int N, int MB>
 static cudaError_t prepare_mb(size_t *smem_out, int *occ) {
   using TR = WsTraits<LOG2M, N>;
   const size_t smem = TR::smem_bytes(2 * MB);
-  cudaError_t e = cudaFuncSetAttribute(k_rx_ws<LOG2M, N, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(k_rx_ws<LOG2M, N, MB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_rx_ws<LOG2M, N, MB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   *smem_out = smem;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_rx_ws<LOG2M, N, MB>, TR::THREADS, smem);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_rx_ws<LOG2M, N, MB, true>, TR::THREADS, smem);
 }
 template <int LOG2M, int N>
 static cudaError_t prepare(uint32_t q, size_t *smem_out, int *occ) {
@@ -27,17 +29,24 @@ static cudaError_t prepare(uint32_t q, size_t *smem_out, int *occ) {
     case 2: return prepare_mb<LOG2M, N, 1>(smem_out, occ);
     case 4: return prepare_mb<LOG2M, N, 2>(smem_out, occ);
     case 6: return prepare_mb<LOG2M, N, 3>(smem_out, occ);
-    default: return prepare_mb<LOG2M, N, 4>(smem_out, occ);
+    default: return cudaErrorInvalidValue;  // 256-QAM: the LLR staging does not fit beside the rings (monolithic kernel)
   }
+}
+template <int LOG2M, int N, int MB>
+static void launch_mb(int grid, size_t smem, cudaStream_t st, const FusedArgs &fa, const DemapConst &dc) {
+  constexpr int T = WsTraits<LOG2M, N>::THREADS;
+  const ChainArgs &a = fa.a;
+  // the usual output set gets the instance without per-task null checks of the output pointers
+  if (a.eq && a.llr && a.bits && a.tx_data && !a.rx_data) k_rx_ws<LOG2M, N, MB, true><<<grid, T, smem, st>>>(fa, dc);
+  else k_rx_ws<LOG2M, N, MB, false><<<grid, T, smem, st>>>(fa, dc);
 }
 template <int LOG2M, int N>
 static void launch(int grid, size_t smem, cudaStream_t st, const FusedArgs &fa, const DemapConst &dc) {
-  constexpr int T = WsTraits<LOG2M, N>::THREADS;
   switch (fa.a.q) {
-    case 2: k_rx_ws<LOG2M, N, 1><<<grid, T, smem, st>>>(fa, dc); break;
-    case 4: k_rx_ws<LOG2M, N, 2><<<grid, T, smem, st>>>(fa, dc); break;
-    case 6: k_rx_ws<LOG2M, N, 3><<<grid, T, smem, st>>>(fa, dc); break;
-    default: k_rx_ws<LOG2M, N, 4><<<grid, T, smem, st>>>(fa, dc); break;
+    case 2: launch_mb<LOG2M, N, 1>(grid, smem, st, fa, dc); break;
+    case 4: launch_mb<LOG2M, N, 2>(grid, smem, st, fa, dc); break;
+    case 6: launch_mb<LOG2M, N, 3>(grid, smem, st, fa, dc); break;
+    default: break;  // never prepared (see prepare)
   }
 }
 cudaError_t ws_prepare(uint32_t l2, uint32_t N, uint32_t q, size_t *smem, int *occ) {
