@@ -607,13 +607,15 @@ class Receiver:
         return out
 
     # -- multi-burst capture (f1 + f2 + decode) --
-    def process_capture(self, capture, max_frames, threshold=0.95, out_mask=OUT_EQ | OUT_RXDATA, tx_data=None):
-        """capture: numpy complex64 [N][n].  Returns (n_found, sync_index[n_found], outputs dict of numpy
-        arrays sized for the bursts found)."""
+    def process_capture(self, capture, max_frames, threshold=0.95, out_mask=OUT_EQ | OUT_RXDATA, tx_data=None, out=None):
+        """capture: numpy complex64 [N][n] (pinned memory makes the copies asynchronous).  out: buffers of
+        alloc_outputs_host(max_frames, out_mask[, pinned=True]) to reuse across calls.  Returns (n_found,
+        sync_index[n_found], outputs dict of numpy arrays sized for the bursts found)."""
         cfg = self.cfg
         capture = np.ascontiguousarray(capture, np.complex64)
         assert capture.shape[0] == cfg.N
-        out = self.alloc_outputs_host(max_frames, out_mask, pinned=False)
+        if out is None:
+            out = self.alloc_outputs_host(max_frames, out_mask, pinned=False)
         tx_data = None if tx_data is None else np.ascontiguousarray(tx_data, np.uint8)
         cnt = np.zeros((cfg.N, 4), np.uint64)
         io = rub_rx_io()

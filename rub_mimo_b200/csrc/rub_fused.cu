@@ -39,7 +39,9 @@ void fused_launch(uint32_t l2, uint32_t N, int grid, size_t smem, cudaStream_t s
 template <int N, int MB>
 static void launch_lean(const ChainArgs &a, const DemapConst &dc, cudaStream_t st) {
   const int llr_stage = 256 * 2 * MB;
-  const size_t smem = (size_t)8 * 2 * (llr_stage + 64);  // 8 warps x 2 staging slots
+  // 8 warps x (2 staging slots + 2 W records of N * 512 + 512 bytes)
+  const size_t smem = (size_t)8 * 2 * (llr_stage + 64) + (DetectLeanTmaW<N>::value ? (size_t)8 * 2 * (N * 512 + 512) : 0);
+  cudaFuncSetAttribute(k_detect_lean<N, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const long long nwork = (long long)a.n_frames * a.D * (a.M / 64);
   k_detect_lean<N, MB><<<(unsigned)((nwork + 7) / 8), 256, smem, st>>>(a, dc, llr_stage);
 }
@@ -52,10 +54,16 @@ static void launch_lean_q(const ChainArgs &a, const DemapConst &dc, cudaStream_t
     default: launch_lean<N, 4>(a, dc, st); break;
   }
 }
-bool detect_lean_launch(const ChainArgs &a, const DemapConst &dc, cudaStream_t st) {
+bool detect_lean_eligible(const ChainArgs &a) {
   if (a.Mo != a.M || (a.M % 64)) return false;
-  if (((uintptr_t)a.llr & 15) || ((uintptr_t)a.bits & 15) || ((uintptr_t)a.eq & 15)) return false;
+  if (((uintptr_t)a.llr & 15) || ((uintptr_t)a.bits & 15) || ((uintptr_t)a.eq & 15) || ((uintptr_t)a.W & 15)) return false;
   if (((uintptr_t)a.rx_data & 1) || ((uintptr_t)a.tx_data & 1)) return false;
+  return a.N == 1 || a.N == 2 || a.N == 4 || a.N == 8;
+}
+// do the weights kernels have to write task records for this call?
+bool detect_lean_records(const ChainArgs &a) { return detect_lean_eligible(a) && a.N >= 4; }
+bool detect_lean_launch(const ChainArgs &a, const DemapConst &dc, cudaStream_t st) {
+  if (!detect_lean_eligible(a) || (a.wrec != 0) != detect_lean_records(a)) return false;
   switch (a.N) {
     case 1: launch_lean_q<1>(a, dc, st); return true;
     case 2: launch_lean_q<2>(a, dc, st); return true;

@@ -26,6 +26,10 @@ struct ChainArgs {
   cf *W;       // [frame][stream][rx][k]
   float *gain; // [frame][stream][k]
   float *isig; // [frame][stream][k]
+  // wrec != 0: the W / gain / isig region (contiguous, starting at W) holds task records instead, one per (frame,
+  // 64-carrier block, stream): W[rx][64] complex, gain[64], isig[64] = N*512 + 512 bytes, fetched by k_detect_lean
+  // with one TMA bulk copy
+  int wrec;
   cf *eq;
   float *llr;
   unsigned char *bits;
@@ -33,6 +37,15 @@ struct ChainArgs {
   const unsigned char *tx_data;
   unsigned long long *counters;
 };
+
+// byte offset of carrier k's entry in the record region (see ChainArgs::wrec): W[s][r] for part = r < N, gain for
+// part = N, isig for part = N + 1
+RUB_HD size_t wrec_offset(int N, int M, long long frame, int s, int k, int part) {
+  const size_t slot = (size_t)N * 512 + 512;
+  const size_t rec = ((size_t)frame * (M >> 6) + (k >> 6)) * N + s;
+  const size_t inner = part < N ? (size_t)part * 512 + (size_t)(k & 63) * 8 : (size_t)N * 512 + (size_t)(part - N) * 256 + (size_t)(k & 63) * 4;
+  return rec * slot + inner;
+}
 
 struct FusedArgs {
   ChainArgs a;

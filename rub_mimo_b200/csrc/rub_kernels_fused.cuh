@@ -589,19 +589,33 @@ __global__ void __launch_bounds__(FusedTraits<LOG2M, N>::THREADS, FusedTraits<LO
 // isig and tx_data come from HBM/L2 (written by k_fft_staged / k_weights).  One warp per (frame,
 // symbol, 64-carrier block); it reads Y once and serves the N streams in turn, one carrier per
 // lane (two half-tasks of 32 carriers per stream): a thread then needs ~80 registers for N = 4,
-// an SM holds 24 warps instead of the 16 a two-carriers-per-lane mapping allows, and the
-// W/gain/isig/tx loads of the next half-task are in flight while the current one is computed.
+// an SM holds 24 warps instead of the 16 a two-carriers-per-lane mapping allows.  W, gain and 1/sigma^2 of a
+// stream's 64 carriers come as one TMA record (one bulk copy into a two-deep per-warp ring, two streams
+// ahead of their use, completed on an mbarrier): no W registers are held across half-tasks and an L2 round trip
+// (the stall that dominated the register-prefetch version) has two half-tasks of work to hide behind.
 // LLRs and packed bits are staged per warp in their final byte order and leave by TMA bulk store.
+template <int N> struct DetectLeanTmaW { static constexpr bool value = N >= 4; };
 template <int N, int MB>
 __global__ void __launch_bounds__(256, (N <= 4 ? 3 : 2)) k_detect_lean(ChainArgs a, DemapConst lutp, int llr_stage_bytes) {
   constexpr int Q = 2 * MB, WARPS = 8;
+  // TMAW: W / gain / isig come as TMA task records (ChainArgs::wrec).  With one or two streams a warp's whole job
+  // is two or four half-tasks and the ring's prologue would be most of it: those keep the register prefetch.
+  constexpr bool TMAW = DetectLeanTmaW<N>::value;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ unsigned cnt[2 * N];
+  __shared__ __align__(8) unsigned long long wbar[WARPS][2];
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   if (tid < 2 * N) cnt[tid] = 0;
+  if (TMAW && lane == 0) {
+    mbar_init(&wbar[warp][0], 1);
+    mbar_init(&wbar[warp][1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_async_smem();
+  }
   __syncthreads();
   const int M = a.M;
+  constexpr int WSLOT = N * 512 + 512;  // W[r][64] complex, gain[64], isig[64] of one stream
   const int blocks_per_sym = M / 64;
   const long long wid = (long long)blockIdx.x * WARPS + warp;            // (frame, symbol, block)
   const long long nwork = (long long)a.n_frames * a.D * blocks_per_sym;
@@ -616,9 +630,23 @@ __global__ void __launch_bounds__(256, (N <= 4 ? 3 : 2)) k_detect_lean(ChainArgs
     const int k0 = kb * 64;
     const long long nsym = a.T + a.D;
     const cf *Yf = a.Y + ((frame * nsym + a.T + d) * N) * M + k0 + lane;
+    // this block's task records, one per stream (ChainArgs::wrec), or the classic arrays at this lane's carrier
+    const unsigned char *wrec0 = reinterpret_cast<const unsigned char *>(a.W) + (TMAW ? wrec_offset(N, M, frame, 0, k0, 0) : 0);
     const cf *Wf = a.W + frame * N * N * M + k0 + lane;
     const float *gf = a.gain + frame * N * M + k0 + lane, *sf = a.isig + frame * N * M + k0 + lane;
     const int stage_stride = llr_stage_bytes + 64;
+    unsigned char *wring = smem_raw + (size_t)WARPS * 2 * stage_stride + (size_t)warp * 2 * WSLOT;
+    // record of stream s_ -> ring slot s_ & 1 (one lane)
+    auto issue_w = [&](int s_) {
+      unsigned char *dst = wring + (s_ & 1) * WSLOT;
+      unsigned long long *bar = &wbar[warp][s_ & 1];
+      mbar_expect_tx(bar, (unsigned)WSLOT);
+      bulk_load(dst, wrec0 + (size_t)s_ * WSLOT, (unsigned)WSLOT, bar, pol_keep);
+    };
+    if (TMAW && lane == 0) {
+      issue_w(0);
+      if (N > 1) issue_w(1);
+    }
     const long long DM = (long long)a.D * M;
     const long long obase = (frame * N * a.D + d) * (long long)M + k0;   // warp-uniform
     float2 y[2][N];
@@ -628,15 +656,18 @@ __global__ void __launch_bounds__(256, (N <= 4 ? 3 : 2)) k_detect_lean(ChainArgs
       for (int r = 0; r < N; r++) y[h][r] = ld_hint2(Yf + (long long)r * M + 32 * h, pol_stream);
     unsigned eb[ErrWords<N>::NW] = {}, es[ErrWords<N>::NW] = {};
     const bool want_llr = a.llr != nullptr;
-    // half-task j = (stream j/2, carriers k0 + 32*(j%2) + lane); the loads of half-task j+1 are
-    // in flight while j is computed
-    struct HalfRegs { float2 w[N]; float g, is; unsigned tx; };
+    // half-task j = (stream j/2, carriers k0 + 32*(j%2) + lane); only the transmitted symbol of the next
+    // half-task is prefetched through a register
+    // (!TMAW: W, gain and isig of the next half-task are prefetched through registers as well)
+    struct HalfRegs { float2 w[TMAW ? 1 : N]; float g, is; unsigned tx; };
     auto load_half = [&](HalfRegs &t, int j) {
       const int s = j >> 1, h = j & 1;
+      if (!TMAW) {
 #pragma unroll
-      for (int r = 0; r < N; r++) t.w[r] = ld_hint2(Wf + (long long)(s * N + r) * M + 32 * h, pol_keep);
-      t.g = ld_hint1(gf + (long long)s * M + 32 * h, pol_keep);
-      t.is = ld_hint1(sf + (long long)s * M + 32 * h, pol_keep);
+        for (int r = 0; r < N; r++) t.w[TMAW ? 0 : r] = ld_hint2(Wf + (long long)(s * N + r) * M + 32 * h, pol_keep);
+        t.g = ld_hint1(gf + (long long)s * M + 32 * h, pol_keep);
+        t.is = ld_hint1(sf + (long long)s * M + 32 * h, pol_keep);
+      }
       t.tx = a.tx_data ? (unsigned)a.tx_data[obase + s * DM + 32 * h + lane] : 0u;
     };
     HalfRegs cur, nxt;
@@ -647,13 +678,23 @@ __global__ void __launch_bounds__(256, (N <= 4 ? 3 : 2)) k_detect_lean(ChainArgs
       const int s = j >> 1, h = j & 1;
       if (j + 1 < 2 * N) load_half(nxt, j + 1);
       unsigned char *slot = smem_raw + (size_t)(warp * 2 + (s & 1)) * stage_stride;
+      const unsigned char *wrec = wring + (s & 1) * WSLOT;
       if (h == 0) {
         if (lane == 0) bulk_wait_read<1>();
         __syncwarp();
+        if (TMAW) mbar_wait(&wbar[warp][s & 1], (unsigned)((s >> 1) & 1));  // this stream's record has landed
       }
       cf wv[N], yv[N];
 #pragma unroll
-      for (int r = 0; r < N; r++) { wv[r] = mk(cur.w[r].x, cur.w[r].y); yv[r] = mk(y[h][r].x, y[h][r].y); }
+      for (int r = 0; r < N; r++) {
+        const float2 t2 = TMAW ? *reinterpret_cast<const float2 *>(wrec + r * 512 + (32 * h + lane) * 8) : cur.w[TMAW ? 0 : r];
+        wv[r] = mk(t2.x, t2.y);
+        yv[r] = mk(y[h][r].x, y[h][r].y);
+      }
+      if (TMAW) {
+        cur.g = *reinterpret_cast<const float *>(wrec + N * 512 + (32 * h + lane) * 4);
+        cur.is = *reinterpret_cast<const float *>(wrec + N * 512 + 256 + (32 * h + lane) * 4);
+      }
       const cf z = cscale(wy_dot<N>(wv, yv), cur.g);
       const unsigned si = slice_axis_refs<MB>(z.x, refs), sq = slice_axis_refs<MB>(z.y, refs);
       const unsigned c = (si << MB) | sq;
@@ -689,6 +730,8 @@ __global__ void __launch_bounds__(256, (N <= 4 ? 3 : 2)) k_detect_lean(ChainArgs
             if ((lane & 7) == 0) store_packed_bits<Q>(slot + llr_stage_bytes + (4 * hh + (lane >> 3)) * Q, v4, p4);
           }
         }
+        // the proxy fence also waits for this lane's reads of the W record (their values went into the products):
+        // the record two streams ahead may overwrite it
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
@@ -696,6 +739,7 @@ __global__ void __launch_bounds__(256, (N <= 4 ? 3 : 2)) k_detect_lean(ChainArgs
           if (a.llr) bulk_store(a.llr + ob * Q, slot, (unsigned)(64 * Q * 4), pol_stream);
           if (a.bits) bulk_store(a.bits + (ob >> 3) * Q, slot + llr_stage_bytes, (unsigned)(8 * Q), pol_stream);
           bulk_commit();
+          if (TMAW && s + 2 < N) issue_w(s + 2);
         }
       }
       if (j + 1 < 2 * N) cur = nxt;

@@ -130,6 +130,30 @@ __global__ void k_ls_comb(ChainArgs a) {
   }
 }
 
+// W / gain / isig of carrier k (zero = null carrier): classic arrays or task records (ChainArgs::wrec)
+template <int N>
+__device__ __forceinline__ void store_weights(const ChainArgs &a, long long frame, int k, const cf *W, const float *gain,
+                                              const float *isig, bool zero) {
+  if (a.wrec) {
+    unsigned char *base = reinterpret_cast<unsigned char *>(a.W);
+#pragma unroll
+    for (int e = 0; e < N * N; e++)
+      *reinterpret_cast<cf *>(base + wrec_offset(N, a.M, frame, e / N, k, e % N)) = zero ? mk(0.f, 0.f) : W[e];
+#pragma unroll
+    for (int s = 0; s < N; s++) {
+      *reinterpret_cast<float *>(base + wrec_offset(N, a.M, frame, s, k, N)) = zero ? 0.f : gain[s];
+      *reinterpret_cast<float *>(base + wrec_offset(N, a.M, frame, s, k, N + 1)) = zero ? 0.f : isig[s];
+    }
+    return;
+  }
+  cf *Wf = a.W + frame * N * N * a.M;
+  float *gf = a.gain + frame * N * a.M, *sf = a.isig + frame * N * a.M;
+#pragma unroll
+  for (int e = 0; e < N * N; e++) Wf[(long long)e * a.M + k] = zero ? mk(0.f, 0.f) : W[e];
+#pragma unroll
+  for (int s = 0; s < N; s++) { gf[(long long)s * a.M + k] = zero ? 0.f : gain[s]; sf[(long long)s * a.M + k] = zero ? 0.f : isig[s]; }
+}
+
 // ---- K3: per-subcarrier ZF / MMSE weights (mimo/framing.cc:826-832, :1344-1367) ---------
 template <int N>
 __global__ void k_weights(ChainArgs a, WeightMode wm) {
@@ -139,24 +163,16 @@ __global__ void k_weights(ChainArgs a, WeightMode wm) {
   const int k = (int)(i % a.M);
   const long long frame = i / a.M;
   const cf *Gf = a.G + frame * N * N * a.M;
-  cf *Wf = a.W + frame * N * N * a.M;
-  float *gf = a.gain + frame * N * a.M, *sf = a.isig + frame * N * a.M;
-  if (a.scnull[k]) {
-#pragma unroll
-    for (int e = 0; e < N * N; e++) Wf[(long long)e * a.M + k] = mk(0.f, 0.f);
-#pragma unroll
-    for (int s = 0; s < N; s++) { gf[(long long)s * a.M + k] = 0.f; sf[(long long)s * a.M + k] = 0.f; }
-    return;
-  }
   cf G[N * N], W[N * N];
   float gain[N], isig[N];
+  if (a.scnull[k]) {
+    store_weights<N>(a, frame, k, W, gain, isig, true);
+    return;
+  }
 #pragma unroll
   for (int e = 0; e < N * N; e++) G[e] = Gf[(long long)e * a.M + k];
   compute_weights<N>(wm, G, W, gain, isig);
-#pragma unroll
-  for (int e = 0; e < N * N; e++) Wf[(long long)e * a.M + k] = W[e];
-#pragma unroll
-  for (int s = 0; s < N; s++) { gf[(long long)s * a.M + k] = gain[s]; sf[(long long)s * a.M + k] = isig[s]; }
+  store_weights<N>(a, frame, k, W, gain, isig, false);
 }
 
 // ---- K2+K3 for the comb estimator in one pass: G never goes to HBM (it is written only when the caller asked
@@ -214,8 +230,6 @@ __global__ void __launch_bounds__(128) k_lscomb_weights(ChainArgs a, WeightMode 
   __syncthreads();
   const int k = kt0 + threadIdx.x;
   if (k >= a.M) return;
-  cf *Wf = a.W + (long long)frame * N * N * a.M;
-  float *gf = a.gain + (long long)frame * N * a.M, *sf = a.isig + (long long)frame * N * a.M;
   cf G[N * N], W[N * N];
   float gain[N], isig[N];
   const float invP = 1.0f / (float)P;
@@ -242,17 +256,11 @@ __global__ void __launch_bounds__(128) k_lscomb_weights(ChainArgs a, WeightMode 
     for (int e = 0; e < N * N; e++) Gf[(long long)e * a.M + k] = G[e];
   }
   if (a.scnull[k]) {
-#pragma unroll
-    for (int e = 0; e < N * N; e++) Wf[(long long)e * a.M + k] = mk(0.f, 0.f);
-#pragma unroll
-    for (int s = 0; s < N; s++) { gf[(long long)s * a.M + k] = 0.f; sf[(long long)s * a.M + k] = 0.f; }
+    store_weights<N>(a, frame, k, W, gain, isig, true);
     return;
   }
   compute_weights<N>(wm, G, W, gain, isig);
-#pragma unroll
-  for (int e = 0; e < N * N; e++) Wf[(long long)e * a.M + k] = W[e];
-#pragma unroll
-  for (int s = 0; s < N; s++) { gf[(long long)s * a.M + k] = gain[s]; sf[(long long)s * a.M + k] = isig[s]; }
+  store_weights<N>(a, frame, k, W, gain, isig, false);
 }
 
 // ---- K4: detect + demap + count (mimo/framing.cc:569-586, mimo/main.cc:1403-1410) --------

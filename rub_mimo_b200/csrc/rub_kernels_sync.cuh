@@ -224,6 +224,23 @@ __global__ void __launch_bounds__(256) k_plateau_ok(const float *__restrict__ y,
   }
 }
 
+// first[t] = first sample of tile t (1024 samples) at which every stream's plateau rule holds, or -1: lets the
+// walk below skip the gaps between bursts a tile at a time
+__global__ void __launch_bounds__(1024) k_plateau_first(const unsigned char *__restrict__ ok, long long n,
+                                                        unsigned long long row_stride, int N, long long *__restrict__ first) {
+  __shared__ long long s_min;
+  const long long i = (long long)blockIdx.x * 1024 + threadIdx.x;
+  if (threadIdx.x == 0) s_min = 0x7fffffffffffffffLL;
+  __syncthreads();
+  bool all = i < n;
+  for (int s = 0; s < N && all; s++) all = ok[(size_t)s * row_stride + i] != 0;
+  long long best = all ? i : 0x7fffffffffffffffLL;
+  for (int o = 16; o; o >>= 1) { const long long t = __shfl_xor_sync(0xffffffffu, best, o); if (t < best) best = t; }
+  if ((threadIdx.x & 31) == 0 && best != 0x7fffffffffffffffLL) atomicMin((unsigned long long *)&s_min, (unsigned long long)best);
+  __syncthreads();
+  if (threadIdx.x == 0) first[blockIdx.x] = s_min == 0x7fffffffffffffffLL ? -1 : s_min;
+}
+
 // The receive loop's state machine over a whole capture (framing.cc:591-651), one CTA: find the first sample
 // at which every stream's plateau rule holds, take the streams' plateau starts (walking back over the metric),
 // sync_index = their mean, skip the access codes and the payload, and search again behind the burst.
@@ -233,8 +250,8 @@ struct PlateauWalk {
   float threshold;
   unsigned max_frames;
 };
-__global__ void __launch_bounds__(1024) k_plateau_walk(const unsigned char *__restrict__ ok, const float *__restrict__ y,
-                                                       unsigned long long row_stride, PlateauWalk w,
+__global__ void __launch_bounds__(1024) k_plateau_walk(const unsigned char *__restrict__ ok, const long long *__restrict__ first,
+                                                       const float *__restrict__ y, unsigned long long row_stride, PlateauWalk w,
                                                        long long *__restrict__ win_off, unsigned long long *__restrict__ syncs,
                                                        unsigned *__restrict__ count) {
   __shared__ long long s_found, s_pos, s_pstart[8];
@@ -246,22 +263,30 @@ __global__ void __launch_bounds__(1024) k_plateau_walk(const unsigned char *__re
   while (cnt < w.max_frames) {
     const long long pos = s_pos;
     long long found = -1;
-    for (long long b0 = pos + w.cp + 1; b0 < w.n; b0 += 1024 * 8) {
-      if (tid == 0) s_found = 0x7fffffffffffffffLL;
-      __syncthreads();
-      long long best = 0x7fffffffffffffffLL;
-      for (int k = 0; k < 8; k++) {
-        const long long i = b0 + tid + (long long)k * 1024;
-        if (i >= w.n) break;
-        bool all = true;
-        for (int s = 0; s < w.N; s++) all = all && ok[(size_t)s * row_stride + i];
-        if (all) { best = i; break; }
+    const long long b0 = pos + w.cp + 1, ntiles = (w.n + 1023) / 1024;
+    if (b0 >= w.n) break;
+    // the rest of the tile the search starts in, sample by sample; then whole tiles through the first[] table
+    for (int phase = 0; phase < 2 && found < 0; phase++) {
+      const long long t0 = b0 / 1024;
+      for (long long c0 = phase ? t0 + 1 : t0; c0 < (phase ? ntiles : t0 + 1) && found < 0; c0 += 1024) {
+        if (tid == 0) s_found = 0x7fffffffffffffffLL;
+        __syncthreads();
+        long long best = 0x7fffffffffffffffLL;
+        if (phase == 0) {
+          const long long i = t0 * 1024 + tid;
+          bool all = i >= b0 && i < w.n;
+          for (int s = 0; s < w.N && all; s++) all = ok[(size_t)s * row_stride + i] != 0;
+          if (all) best = i;
+        } else {
+          const long long t = c0 + tid;
+          if (t < ntiles && first[t] >= 0) best = first[t];
+        }
+        for (int o = 16; o; o >>= 1) { const long long t = __shfl_xor_sync(0xffffffffu, best, o); if (t < best) best = t; }
+        if ((tid & 31) == 0 && best != 0x7fffffffffffffffLL) atomicMin((unsigned long long *)&s_found, (unsigned long long)best);
+        __syncthreads();
+        if (s_found != 0x7fffffffffffffffLL) found = s_found;
+        __syncthreads();
       }
-      for (int o = 16; o; o >>= 1) { const long long t = __shfl_xor_sync(0xffffffffu, best, o); if (t < best) best = t; }
-      if ((tid & 31) == 0 && best != 0x7fffffffffffffffLL) atomicMin((unsigned long long *)&s_found, (unsigned long long)best);
-      __syncthreads();
-      if (s_found != 0x7fffffffffffffffLL) { found = s_found; break; }
-      __syncthreads();
     }
     if (found < 0) break;
     // plateau start of every stream: the run of above-threshold samples that contains found, clipped at pos

@@ -19,6 +19,9 @@ size_t ws_sign_bytes(uint32_t log2M, uint32_t N, uint32_t nac);
 void ws_pack_signs(uint32_t log2M, uint32_t N, uint32_t nac, const float *sgn, unsigned char *out);
 void ws_launch(uint32_t log2M, uint32_t N, int grid, size_t smem, cudaStream_t st, const FusedArgs &fa, const DemapConst &dc);
 // block-mapped detect kernel of the staged path (rub_kernels_fused.cuh: k_detect_lean)
+// (its W / gain / isig come as task records: the weights kernels are told through ChainArgs::wrec)
+bool detect_lean_eligible(const ChainArgs &a);
+bool detect_lean_records(const ChainArgs &a);
 bool detect_lean_launch(const ChainArgs &a, const DemapConst &dc, cudaStream_t st);
 
 }  // namespace rub

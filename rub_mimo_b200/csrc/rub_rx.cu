@@ -409,6 +409,7 @@ static rub_status run_staged(rub_rx *h, ChainArgs a, const rub_rx_io *io, uint32
     if (a.bits) b.bits = a.bits + (size_t)f0 * c.N * c.D * c.row_bytes;
     if (a.rx_data) b.rx_data = a.rx_data + f0 * per_sym;
     if (a.tx_data) b.tx_data = a.tx_data + f0 * per_sym;
+    b.wrec = detect_lean_records(b) ? 1 : 0;  // k_detect_lean reads W / gain / isig as task records
     cudaError_t ferr = cudaSuccess;
     switch (c.log2M) {
       case 6: launch_fft<6>(b, h->stream, &ferr); break;
@@ -888,6 +889,7 @@ extern "C" rub_status rub_rx_process_capture(rub_rx *h, const float *capture, ui
   size_t need = 0;
   auto carve = [&](size_t bytes) { const size_t o = need; need += al(bytes); return o; };
   const size_t o_cap = carve(sizeof(cf) * n * c.N), o_y = carve(sizeof(float) * n * c.N), o_ok = carve(n * c.N),
+               o_first = carve(sizeof(long long) * ((n + 1023) / 1024)),
                o_off = carve(sizeof(long long) * max_frames), o_syn = carve(sizeof(unsigned long long) * max_frames), o_cnt = carve(256),
                o_keys = carve(sizeof(unsigned long long) * (size_t)max_frames * c.N * slots),
                o_tim = carve(sizeof(int32_t) * (size_t)max_frames * c.N * c.T), o_pay = carve(sizeof(int32_t) * max_frames),
@@ -923,8 +925,10 @@ extern "C" rub_status rub_rx_process_capture(rub_rx *h, const float *capture, ui
     PlateauWalk w;
     w.n = (long long)n; w.L = (long long)L; w.acb_len = (long long)acb_len; w.tx_sig_len = (long long)tx_sig_len; w.Wlen = (long long)Wlen;
     w.N = (int)c.N; w.cp = (int)c.cp; w.threshold = threshold; w.max_frames = max_frames;
-    k_plateau_walk<<<1, 1024, 0, h->stream>>>(d_ok, d_y, n, w, d_off, d_syn, d_cnt);
-    h->launches += 2;
+    long long *d_first = (long long *)(base + o_first);
+    k_plateau_first<<<(unsigned)((n + 1023) / 1024), 1024, 0, h->stream>>>(d_ok, (long long)n, n, (int)c.N, d_first);
+    k_plateau_walk<<<1, 1024, 0, h->stream>>>(d_ok, d_first, d_y, n, w, d_off, d_syn, d_cnt);
+    h->launches += 3;
     CUDA_TRY(cudaGetLastError());
   }
   uint32_t F = 0;
