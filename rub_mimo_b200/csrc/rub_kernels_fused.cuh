@@ -71,6 +71,25 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// try_wait with a suspend-time hint: the warp is parked by the hardware until the phase completes or the hint
+// (nanoseconds) expires, instead of re-issuing the test every few cycles
+__device__ __forceinline__ bool mbar_try_wait_hint(unsigned long long *bar, unsigned parity, unsigned ns) {
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_parked(unsigned long long *bar, unsigned parity) {
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+  }
+}
 // A consumer that is expected to wait for a while (the detect warps waiting for the FFT warps): a bare
 // try_wait loop returns after a few cycles and its polling takes issue slots from the very warps it waits for
 // (measured: a quarter of the kernel's issued instructions), so sleep between polls.

@@ -31,7 +31,7 @@
 
 #ifndef RUB_WS_ABLATE
 #define RUB_WS_ABLATE 0  // measurement builds only (wrong results): 1 FFT warps skip the transform, 2 detect warps skip
-                         // detection, 4 no G scratch stores, 8 no W/gain/isig scratch stores
+                         // detection, 4 no G scratch stores, 8 no W/gain/isig scratch stores, 16 no gain/isig/tx loads
 #endif
 #ifndef RUB_WS_BACKOFF_NS
 #define RUB_WS_BACKOFF_NS 100
@@ -43,7 +43,7 @@ template <int LOG2M, int N>
 struct WsTraits {
   using FF = Fft<LOG2M>;
   using PL = FftPlan<LOG2M>;
-  static constexpr int M = FF::M, NT = FF::NT, PAD = fft_padded_size(M);
+  static constexpr int M = FF::M, NT = FF::NT, PAD = M;  // row stride: the stage-0 -> stage-1 exchange is XOR-swizzled, not padded
   static constexpr int FFT_WARPS = NT / 32;
   static constexpr int BLOCKS = M / 64;                         // 64-carrier blocks per OFDM symbol
   static constexpr int DET_WARPS = BLOCKS < 16 ? BLOCKS : 16;
@@ -57,14 +57,15 @@ struct WsTraits {
   static constexpr int LAUNCH_REGS = 65536 / THREADS / 8 * 8;
   static constexpr int DET_REGS = LAUNCH_REGS - 8;
   static constexpr int FFT_REGS = (LAUNCH_REGS + 8 * DET_THREADS / NT) / 8 * 8;
-  static constexpr int WREC = N * 64;                           // W record of one detection task: [r][64 carriers]
+  static constexpr int WREC = N * 64 + 64;                      // task record in cf units: W[r][64], gain[64] f32, isig[64] f32
+  static_assert(PL::R0 == 16 && PL::R1 == 16 && M / NT == 16, "the swizzled exchange below is written for 16-point threads");
   static_assert(PL::NSTG == 3, "three-stage plans only");
   static_assert(NT % 128 == 0 && DET_THREADS % 128 == 0, "roles are whole warpgroups (setmaxnreg)");
   static_assert(N >= 2 && N <= 4, "FFT barrier scheme needs two antenna regions; packed counters hold four streams");
   static_assert(KPW * DET_WARPS == BLOCKS, "block split");
   static size_t smem_bytes(int q) {
     return (size_t)2 * BUF_ELEMS * sizeof(cf) /* payload ring */ + (size_t)(M + PAD) * sizeof(cf) /* training: landing + work row */ +
-           (size_t)DET_WARPS * (256 * q) /* LLR staging */ + (size_t)DET_WARPS * WREC * sizeof(cf) /* W records, one per detect warp */ +
+           (size_t)DET_WARPS * (256 * q) /* LLR staging */ + (size_t)DET_WARPS * WREC * sizeof(cf) /* task records, one per detect warp */ +
            (size_t)(8 + DET_WARPS) * 8 + 16 /* mbarriers, counters */;
   }
 };
@@ -99,6 +100,27 @@ __device__ __forceinline__ unsigned atom_add_acq_rel_smem(unsigned *p, unsigned 
   unsigned old;
   asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
   return old;
+}
+
+// Exchange between the first and the second FFT stage without padding: element idx sits at
+// (idx & ~15) | ((idx ^ (idx >> 4)) & 15).  Stage 0 (radix 16, stride 1): thread j writes idx = 16 j + t, i.e. the
+// byte address (16 j + (j & 15)) * 8 ^ (t * 8) of a 128-byte aligned row: one LOP3 per element, and 16 consecutive
+// lanes hit 16 different 8-byte banks for every t.  Stage 1 (radix 16, stride 16) reads idx = j + 128 t: the low
+// nibble is (j & 15) ^ ((j >> 4) | ((t & 1) << 3)), two base addresses and immediate offsets.
+template <int M>
+__device__ __forceinline__ void ws_s0_store(int j, const cf *v, cf *row) {
+  const unsigned a = smem_u32(row) + (unsigned)((16 * j + (j & 15)) * 8);
+#pragma unroll
+  for (int t = 0; t < 16; t++)
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a ^ (unsigned)(t * 8)), "f"(v[t].x), "f"(v[t].y) : "memory");
+}
+template <int M>
+__device__ __forceinline__ void ws_s1_load(int j, const cf *row, cf *v) {
+  static_assert(M == 2048, "Q = M / 16 = 128 and j < 128");
+  const int a0 = (j & ~15) + ((j & 15) ^ (j >> 4));
+  const cf *p0 = row + a0, *p1 = row + (a0 ^ 8);
+#pragma unroll
+  for (int t = 0; t < 16; t++) v[t] = (t & 1) ? p1[128 * t] : p0[128 * t];
 }
 
 // W*y and gain of one detection task: stream s of a 64-carrier block (lane = 2 adjacent carriers)
@@ -286,12 +308,12 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
         buf = work;
 
         // the G scratch is free once the weights of the previous frame have been computed from it
-        if (u == 0 && f >= 1) mbar_wait(&mbar[7], (unsigned)((f - 1) & 1));
-        mbar_wait(&mbar[4], (unsigned)(ug & 1));
+        if (u == 0 && f >= 1) mbar_wait_parked(&mbar[7], (unsigned)((f - 1) & 1));
+        mbar_wait_parked(&mbar[4], (unsigned)(ug & 1));
       } else {
         f = pg / D;
         buf = ring + (size_t)(pg & 1) * TR::BUF_ELEMS;
-        mbar_wait(&mbar[pg & 1], (unsigned)((pg >> 1) & 1));
+        mbar_wait_parked(&mbar[pg & 1], (unsigned)((pg >> 1) & 1));
       }
       // training: the sign bytes of this thread's carriers (one per last-stage butterfly), requested early
       unsigned sgb[B2];
@@ -316,14 +338,14 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
         FF::S0::compute(ft, v, nullptr);
         named_bar(1, NT);
         if (training && tid == 0) issue_training(ug + 1);
-        FF::S0::template store<true, false>(ft, v, reg, 1.f);
+        ws_s0_store<M>(ft, v, reg);
       }
       FF::S1::load_twiddles(ft, a.tw + TW::OFF1, tw);
       if (training) named_bar(1, NT);
 #pragma unroll 1
       for (int r = 0; r < nr; r++) {
         cf *reg = buf + (size_t)r * PAD;
-        FF::S1::template load<true>(ft, reg, v);
+        ws_s1_load<M>(ft, reg, v);
         named_bar(1, NT);
         FF::S1::compute_pre(v, tw);
         // unpadded: NS1 consecutive lanes write consecutive elements (conflict free without the pad), and the last
@@ -430,9 +452,9 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
   int pg = 0;
   for (int f = 0; f < nf; f++) {
     const long long frame = (long long)blockIdx.x + (long long)f * gridDim.x;
-    cf *Wc = fa.scratchW + (size_t)blockIdx.x * N * N * M;
+    // task records of this CTA: [stream][64-carrier block]{ W[rx][64] complex, gain[64], isig[64] }
+    cf *Wc = fa.scratchW + (size_t)blockIdx.x * N * KB * TR::WREC;
     const cf *Gc = fa.scratchAcc + (size_t)blockIdx.x * N * N * M;
-    float *gc = fa.scratchG + (size_t)blockIdx.x * 2 * N * M, *ic = gc + (size_t)N * M;
     // this frame's outputs; inside a frame 32-bit element offsets do ((stream * D + symbol) * M + carrier)
     const long long fbase = frame * N * (long long)D * M;
     cf *const eqf = (FULL || a.eq) ? a.eq + fbase : nullptr;
@@ -442,7 +464,7 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
     const unsigned char *const txf = (FULL || a.tx_data) ? a.tx_data + fbase : nullptr;
     const int DMi = D * M;
     // ---------------- weights (mimo/framing.cc:817-832) ----------------
-    mbar_wait_backoff(&mbar[6], (unsigned)(f & 1), RUB_WS_BACKOFF_NS);  // G(f) is complete (written by the FFT warps)
+    mbar_wait_parked(&mbar[6], (unsigned)(f & 1));  // G(f) is complete (written by the FFT warps)
     if (f > 0) named_bar(2, DET_THREADS);     // every detect warp is done reading the previous frame's W
 #pragma unroll 1
     for (int k = dtid; k < M; k += DET_THREADS) {
@@ -458,18 +480,22 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
         for (int e = 0; e < N * N; e++) a.G[(frame * N * N + e) * M + k] = G[e];
       }
       compute_weights<N>(fa.wm, G, W, gain, isig);
-      // W in task records: [stream][64-carrier block][rx][64], one 64*N*8-byte bulk copy per detection task
+      // task records: one bulk copy per detection task brings W, gain and 1/sigma^2 of a stream's 64 carriers
 #if (RUB_WS_ABLATE & 8)  // measurement only: no scratch stores
       if (k < 0)
 #endif
 #pragma unroll
       for (int e = 0; e < N * N; e++)
-        st_hint2(Wc + ((size_t)((e / N) * KB + (k >> 6)) * N + (e % N)) * 64 + (k & 63), make_float2(W[e].x, W[e].y), pol_keep);
+        st_hint2(Wc + (size_t)((e / N) * KB + (k >> 6)) * TR::WREC + (e % N) * 64 + (k & 63), make_float2(W[e].x, W[e].y), pol_keep);
 #if (RUB_WS_ABLATE & 8)
       if (k < 0)
 #endif
 #pragma unroll
-      for (int s = 0; s < N; s++) { st_hint1(gc + (size_t)s * M + k, gain[s], pol_keep); st_hint1(ic + (size_t)s * M + k, isig[s], pol_keep); }
+      for (int s = 0; s < N; s++) {
+        float *rec = reinterpret_cast<float *>(Wc + (size_t)(s * KB + (k >> 6)) * TR::WREC + N * 64);
+        st_hint1(rec + (k & 63), gain[s], pol_keep);
+        st_hint1(rec + 64 + (k & 63), isig[s], pol_keep);
+      }
     }
     // the W records are read through the async proxy (TMA): order this thread's generic-proxy stores before it
     __threadfence();
@@ -481,7 +507,7 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
     // W record of detection task (stream s, block kb of this warp) -> this warp's buffer (one lane)
     auto issue_w = [&](int s_, int kb_) {
       mbar_expect_tx(wrdy, (unsigned)(TR::WREC * sizeof(cf)));
-      bulk_load(wbuf, Wc + ((size_t)(s_ * KB + dwarp + kb_ * DET_WARPS) * N) * 64, (unsigned)(TR::WREC * sizeof(cf)), wrdy, pol_keep);
+      bulk_load(wbuf, Wc + (size_t)(s_ * KB + dwarp + kb_ * DET_WARPS) * TR::WREC, (unsigned)(TR::WREC * sizeof(cf)), wrdy, pol_keep);
     };
     if (lane == 0) issue_w(0, 0);
 
@@ -490,7 +516,6 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
     for (int d = 0; d < D; d++, pg++) {
       const int b = pg & 1;
       const cf *buf = ring + (size_t)b * TR::BUF_ELEMS;
-      int gi = koff;                    // gain[s][k] index of the task; isig follows N*M floats later
       int ob = 0;                       // element offset of the task's block from the symbol's (stream 0, block 0)
       // this symbol's output positions of the lane / the warp's block, kept in registers (the compiler would
       // otherwise rebuild them from the kernel arguments in every task)
@@ -501,14 +526,16 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
       unsigned char *bitd = bitsf + ((d0 >> 3) + (lane >> 2)) * Q;
       unsigned char *llrd = llrf + (size_t)d0 * (Q * 4);
       asm volatile("" : "+l"(eqd), "+l"(txd), "+l"(bitd), "+l"(llrd));
-      float2 tg, tis;                   // gain, 1/sigma_eff^2 of the lane's two carriers
-      unsigned txv = 0;                 // transmitted symbols of the two carriers of the task
-      auto load_w = [&]() {  // gain, 1/sigma^2 and the reference symbols of the next task (W itself comes by TMA)
-        tg = ld_hint2(gc + gi, pol_keep);
-        tis = ld_hint2(gc + gi + N * M, pol_keep);
+      // transmitted symbols of the lane's two carriers: the only plain load of the task loop, requested a whole
+      // task before its use and AFTER the LLR store's proxy fence (which waits for loads in flight)
+      unsigned txv = 0;
+      auto load_tx = [&]() {
+#if (RUB_WS_ABLATE & 16)  // measurement only: no tx loads
+        return;
+#endif
         if (FULL || txf) txv = ld_hint_u16(txd + ob, pol_stream);
       };
-      load_w();  // first task: requested before Y is needed
+      load_tx();  // first task: requested before Y is needed
       if ((FULL || txf) && lane < KPW * N) {
         // the reference symbols of this warp's tasks of the NEXT payload symbol: pull their lines into L2 now so
         // that the 2-byte loads riding with the gain loads never wait for HBM
@@ -516,7 +543,7 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
         if (d == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(tp));
         if (d + 1 < D) asm volatile("prefetch.global.L2 [%0];" ::"l"(tp + M));
       }
-      mbar_wait_backoff(&mbar[2 + b], (unsigned)((pg >> 1) & 1), RUB_WS_BACKOFF_NS);
+      mbar_wait_parked(&mbar[2 + b], (unsigned)((pg >> 1) & 1));
       int it = 0;
 #pragma unroll 1
       for (int kb = 0; kb < KPW; kb++) {
@@ -541,14 +568,13 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
         for (int s = 0; s < N; s++, it++) {
           cf z0, z1;
           TaskRegs<N> w;
-          w.g = tg;
-          const float2 is = tis;
-          const unsigned tx2 = txv;
           const int obc = ob;
-          mbar_wait(wrdy, wn & 1u);
+          mbar_wait_parked(wrdy, wn & 1u);
           wn++;
 #pragma unroll
           for (int r = 0; r < N; r++) w.w[r] = *reinterpret_cast<const float4 *>(wbuf + r * 64 + 2 * lane);
+          w.g = *reinterpret_cast<const float2 *>(reinterpret_cast<const float *>(wbuf + N * 64) + 2 * lane);
+          const float2 is = *reinterpret_cast<const float2 *>(reinterpret_cast<const float *>(wbuf + N * 64) + 64 + 2 * lane);
           ws_dot<N>(w, y4, z0, z1);
           // The record of the next task of this frame (the next symbol starts over at task 0).  The proxy fence
           // waits for this lane's loads of the buffer (their values went into the products above) before the
@@ -562,10 +588,8 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
           const unsigned rx2 = ws_hard<MB, FULL>(refs, z0, z1, (FULL || eqf) ? eqd + obc : nullptr, rxd ? rxd + obc : nullptr,
                                                  (FULL || bitsf) ? reinterpret_cast<unsigned short *>(bitd + (obc >> 3) * Q) : nullptr,
                                                  pol_stream, lane);
-          // gain / isig / tx of the next task land in the registers the products released
-          if (s + 1 < N) { gi += M; ob += DMi; }
-          else { gi += KSTEP - (N - 1) * M; ob += KSTEP - (N - 1) * DMi; }
-          if (it + 1 < KPW * N) load_w();
+          if (s + 1 < N) ob += DMi;
+          else ob += KSTEP - (N - 1) * DMi;
           if (FULL || llrf) {
             // the bulk store of the previous task must have read the staging slot
             if (lane == 0) bulk_wait_read<0>();
@@ -579,11 +603,12 @@ __global__ void __launch_bounds__(WsTraits<LOG2M, N>::THREADS, 1) k_rx_ws(FusedA
             }
           }
           if (FULL || txf) {
-            const unsigned x = rx2 ^ tx2;
+            const unsigned x = rx2 ^ txv;
             const unsigned vb = (unsigned)__popc(x) << (16 * (s & 1));
             const unsigned vs = (((x & 0xffu) != 0u ? 1u : 0u) + ((x >> 8) != 0u ? 1u : 0u)) << (16 * (s & 1));
             if (s & 2) { eb1 += vb; es1 += vs; } else { eb0 += vb; es0 += vs; }
           }
+          if (it + 1 < KPW * N) load_tx();  // the next task's (ob has moved on)
         }
       }
       if ((FULL || a.tx_data) && (++since_flush == flush_every || d == D - 1)) { flush_counts(since_flush); since_flush = 0; }

@@ -460,7 +460,8 @@ static rub_status run_fused(rub_rx *h, const ChainArgs &a, uint32_t n_frames, bo
     h->fused_grid = grid;
     h->fused_smem = smem;
     // per-CTA scratch: G -> W in place, gain, isig (re-read D times per frame: L2 resident)
-    CUDA_TRY(cudaMalloc(&h->d_fW, (size_t)grid * c.N * c.N * c.M * sizeof(cf)));
+    // (the warp-specialised kernel keeps W, gain and isig together as task records in the first buffer)
+    CUDA_TRY(cudaMalloc(&h->d_fW, (size_t)grid * (c.N * c.N * c.M * sizeof(cf) + (h->ws ? 2 * c.N * c.M * sizeof(float) : 0))));
     CUDA_TRY(cudaMalloc(&h->d_fG, (size_t)grid * 2 * c.N * c.M * sizeof(float)));
     if (h->ws) {
       // the warp-specialised kernel estimates frame f+1 while frame f is detected
