@@ -103,3 +103,29 @@ def test_capture_with_reused_pinned_buffers():
         assert n1 == n0 and np.array_equal(sync1, sync0)
         assert np.array_equal(out1["eq"], out0["eq"]) and np.array_equal(out1["rx_data"], out0["rx_data"])
     rx.close()
+
+
+@pytest.mark.parametrize("D,nac,cp,frames", [(1, 1, 152, 3), (2, 3, 152, 149), (3, 5, 0, 2), (14, 2, 152, 301), (6, 1, 64, 1)])
+def test_ws_kernel_frame_and_symbol_count_edges(D, nac, cp, frames):
+    """k_rx_ws schedules the training symbols of frame f+1 between the payload symbols of frame f from the third
+    on: one or two payload symbols per frame, one to five access codes, zero cyclic prefix, one frame for 148
+    CTAs, and batches that leave a ragged tail all have to agree with the oracle bit for bit."""
+    import torch
+    cfg = rub.Config(M=2048, cp_len=cp, num_streams=4, num_access_codes=nac, num_data_symbols=D,
+                     modulation=rub.MOD_QAM64, detector=rub.DET_MMSE, flags=rub.FLAG_MMSE_UNBIASED)
+    U = min(frames, 3)
+    cfg, S1, iq_u, tx_u = make_case(cfg, U, seed=D * 100 + nac, n_taps=4 if cp else 1, snr_db=29.0)
+    ref = oracle_run(cfg, S1, iq_u, tx_u)
+    idx = np.arange(frames) % U
+    rx = rub.Receiver(cfg, S1)
+    rx.set_path(rub.PATH_FUSED)
+    mask = rub.OUT_EQ | rub.OUT_LLR | rub.OUT_BITS | rub.OUT_G
+    for _ in range(2):   # twice: the second launch reuses the scratch the first one left behind
+        out = rx.process_batch(torch.from_numpy(iq_u[idx]).cuda(), out_mask=mask, tx_data=torch.from_numpy(tx_u[idx]).cuda())
+        rx.sync()
+        assert rx.last_kernel() == "k_rx_ws"
+        for k in ("eq", "llr", "bits", "G"):
+            assert np.array_equal(out[k].cpu().numpy(), ref[k][idx]), k
+    per = np.stack([oracle_run(cfg, S1, iq_u[i:i + 1], tx_u[i:i + 1])["counters"] for i in range(U)])
+    assert np.array_equal(rx.read_counters(), 2 * per[idx].sum(axis=0))
+    rx.close()
