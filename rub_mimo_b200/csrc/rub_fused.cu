@@ -40,7 +40,7 @@ template <int N, int MB>
 static void launch_lean(const ChainArgs &a, const DemapConst &dc, cudaStream_t st) {
   const int llr_stage = 256 * 2 * MB;
   // 8 warps x (2 staging slots + 2 W records of N * 512 + 512 bytes)
-  const size_t smem = (size_t)8 * 2 * (llr_stage + 64) + (DetectLeanTmaW<N>::value ? (size_t)8 * 2 * (N * 512 + 512) : 0);
+  const size_t smem = (size_t)8 * 2 * (llr_stage + 64) + (DetectLeanTmaW<N>::value ? (size_t)8 * 2 * (N * 512 + 512 + 64) : 0);
   cudaFuncSetAttribute(k_detect_lean<N, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const long long nwork = (long long)a.n_frames * a.D * (a.M / 64);
   k_detect_lean<N, MB><<<(unsigned)((nwork + 7) / 8), 256, smem, st>>>(a, dc, llr_stage);
@@ -58,6 +58,7 @@ bool detect_lean_eligible(const ChainArgs &a) {
   if (a.Mo != a.M || (a.M % 64)) return false;
   if (((uintptr_t)a.llr & 15) || ((uintptr_t)a.bits & 15) || ((uintptr_t)a.eq & 15) || ((uintptr_t)a.W & 15)) return false;
   if (((uintptr_t)a.rx_data & 1) || ((uintptr_t)a.tx_data & 1)) return false;
+  if (a.N >= 4 && ((uintptr_t)a.tx_data & 15)) return false;  // tx_data rides in the TMA ring slot
   return a.N == 1 || a.N == 2 || a.N == 4 || a.N == 8;
 }
 // do the weights kernels have to write task records for this call?

@@ -635,6 +635,7 @@ __global__ void __launch_bounds__(256, (N <= 4 ? 3 : 2)) k_detect_lean(ChainArgs
   __syncthreads();
   const int M = a.M;
   constexpr int WSLOT = N * 512 + 512;  // W[r][64] complex, gain[64], isig[64] of one stream
+  constexpr int RSLOT = WSLOT + 64;     // ring slot: the record + the 64 transmitted symbols of the block (tx_data)
   const int blocks_per_sym = M / 64;
   const long long wid = (long long)blockIdx.x * WARPS + warp;            // (frame, symbol, block)
   const long long nwork = (long long)a.n_frames * a.D * blocks_per_sym;
@@ -649,25 +650,26 @@ __global__ void __launch_bounds__(256, (N <= 4 ? 3 : 2)) k_detect_lean(ChainArgs
     const int k0 = kb * 64;
     const long long nsym = a.T + a.D;
     const cf *Yf = a.Y + ((frame * nsym + a.T + d) * N) * M + k0 + lane;
+    const long long DM = (long long)a.D * M;
+    const long long obase = (frame * N * a.D + d) * (long long)M + k0;   // warp-uniform
     // this block's task records, one per stream (ChainArgs::wrec), or the classic arrays at this lane's carrier
     const unsigned char *wrec0 = reinterpret_cast<const unsigned char *>(a.W) + (TMAW ? wrec_offset(N, M, frame, 0, k0, 0) : 0);
     const cf *Wf = a.W + frame * N * N * M + k0 + lane;
     const float *gf = a.gain + frame * N * M + k0 + lane, *sf = a.isig + frame * N * M + k0 + lane;
     const int stage_stride = llr_stage_bytes + 64;
-    unsigned char *wring = smem_raw + (size_t)WARPS * 2 * stage_stride + (size_t)warp * 2 * WSLOT;
+    unsigned char *wring = smem_raw + (size_t)WARPS * 2 * stage_stride + (size_t)warp * 2 * RSLOT;
     // record of stream s_ -> ring slot s_ & 1 (one lane)
     auto issue_w = [&](int s_) {
-      unsigned char *dst = wring + (s_ & 1) * WSLOT;
+      unsigned char *dst = wring + (s_ & 1) * RSLOT;
       unsigned long long *bar = &wbar[warp][s_ & 1];
-      mbar_expect_tx(bar, (unsigned)WSLOT);
+      mbar_expect_tx(bar, (unsigned)(a.tx_data ? RSLOT : WSLOT));
       bulk_load(dst, wrec0 + (size_t)s_ * WSLOT, (unsigned)WSLOT, bar, pol_keep);
+      if (a.tx_data) bulk_load(dst + WSLOT, a.tx_data + obase + s_ * DM, 64u, bar, pol_stream);
     };
     if (TMAW && lane == 0) {
       issue_w(0);
       if (N > 1) issue_w(1);
     }
-    const long long DM = (long long)a.D * M;
-    const long long obase = (frame * N * a.D + d) * (long long)M + k0;   // warp-uniform
     float2 y[2][N];
 #pragma unroll
     for (int h = 0; h < 2; h++)
@@ -687,7 +689,7 @@ __global__ void __launch_bounds__(256, (N <= 4 ? 3 : 2)) k_detect_lean(ChainArgs
         t.g = ld_hint1(gf + (long long)s * M + 32 * h, pol_keep);
         t.is = ld_hint1(sf + (long long)s * M + 32 * h, pol_keep);
       }
-      t.tx = a.tx_data ? (unsigned)a.tx_data[obase + s * DM + 32 * h + lane] : 0u;
+      t.tx = (a.tx_data && !TMAW) ? (unsigned)a.tx_data[obase + s * DM + 32 * h + lane] : 0u;
     };
     HalfRegs cur, nxt;
     load_half(cur, 0);
@@ -697,7 +699,7 @@ __global__ void __launch_bounds__(256, (N <= 4 ? 3 : 2)) k_detect_lean(ChainArgs
       const int s = j >> 1, h = j & 1;
       if (j + 1 < 2 * N) load_half(nxt, j + 1);
       unsigned char *slot = smem_raw + (size_t)(warp * 2 + (s & 1)) * stage_stride;
-      const unsigned char *wrec = wring + (s & 1) * WSLOT;
+      const unsigned char *wrec = wring + (s & 1) * RSLOT;
       if (h == 0) {
         if (lane == 0) bulk_wait_read<1>();
         __syncwarp();
@@ -713,6 +715,7 @@ __global__ void __launch_bounds__(256, (N <= 4 ? 3 : 2)) k_detect_lean(ChainArgs
       if (TMAW) {
         cur.g = *reinterpret_cast<const float *>(wrec + N * 512 + (32 * h + lane) * 4);
         cur.is = *reinterpret_cast<const float *>(wrec + N * 512 + 256 + (32 * h + lane) * 4);
+        if (a.tx_data) cur.tx = wrec[WSLOT + 32 * h + lane];
       }
       const cf z = cscale(wy_dot<N>(wv, yv), cur.g);
       const unsigned si = slice_axis_refs<MB>(z.x, refs), sq = slice_axis_refs<MB>(z.y, refs);
@@ -727,8 +730,14 @@ __global__ void __launch_bounds__(256, (N <= 4 ? 3 : 2)) k_detect_lean(ChainArgs
         const float kk = lutp.k4 * cur.is;
         llr_axis<MB>(z.x, kk, lutp, l);
         llr_axis<MB>(z.y, kk, lutp, l + MB);
+        if (MB % 2 == 0) {  // 16-byte stores: half the shared-memory wavefronts of the 8-byte ones at this lane stride
 #pragma unroll
-        for (int b = 0; b < MB; b++) lp[b] = make_float2(l[2 * b], l[2 * b + 1]);
+          for (int b = 0; b < MB / 2; b++)
+            reinterpret_cast<float4 *>(lp)[b] = make_float4(l[4 * b], l[4 * b + 1], l[4 * b + 2], l[4 * b + 3]);
+        } else {
+#pragma unroll
+          for (int b = 0; b < MB; b++) lp[b] = make_float2(l[2 * b], l[2 * b + 1]);
+        }
       }
       if (a.tx_data) {
         const unsigned x = symh[h] ^ cur.tx;

@@ -181,7 +181,7 @@ __global__ void k_weights(ChainArgs a, WeightMode wm) {
 // entries with the expressions of k_ls_comb (bit-identical) and goes on with compute_weights<N>.
 template <int N>
 __global__ void __launch_bounds__(128) k_lscomb_weights(ChainArgs a, WeightMode wm, int write_G) {
-  constexpr int TPB = 128, U = 3;
+  constexpr int TPB = 128, U = (N >= 8 ? 9 : N >= 4 ? 6 : 3);  // pilot entries per thread whose loads are in flight together
   extern __shared__ __align__(16) unsigned char sm_raw[];
   cf *pil = reinterpret_cast<cf *>(sm_raw);  // [N*N][J]
   const int P = a.P, lp = 31 - __clz(P), np = a.M >> lp, J = (TPB >> lp) + 2;  // P | M and M = 2^m: P is a power of two
@@ -191,7 +191,8 @@ __global__ void __launch_bounds__(128) k_lscomb_weights(ChainArgs a, WeightMode 
   const float invJ = 1.0f / (float)J;
   const long long nsym = a.T + a.D;
   const bool q1 = (a.flags & RUB_FLAG_Q1_IDENTITY_INIT) != 0;
-  // pilots of the tile, U entries per thread at a time so that their loads are in flight together; the sums are
+  // pilots of the tile, U entries per thread and two access codes at a time so that their loads are in flight
+  // together (one or two round trips to L2 per CTA instead of one per entry and code); the sums are
   // comb_pilot()'s, in its order
   for (int e0 = threadIdx.x; e0 < E; e0 += U * TPB) {
     int r[U], t[U], kp[U];
@@ -210,18 +211,22 @@ __global__ void __launch_bounds__(128) k_lscomb_weights(ChainArgs a, WeightMode 
       ok[u] = e < E && i < np;
       acc[u] = mk((q1 && r[u] == t[u]) ? 1.0f : 0.0f, 0.f);
     }
-    for (int c = 0; c < a.nac; c++) {
-      cf X[U];
-      float sg[U];
+    for (int c0 = 0; c0 < a.nac; c0 += 2) {
+      cf X[2][U];
+      float sg[2][U];
 #pragma unroll
-      for (int u = 0; u < U; u++)
-        if (ok[u]) {
-          X[u] = a.Y[(((long long)frame * nsym + c) * a.N + r[u]) * a.M + kp[u]];
-          sg[u] = a.sgn[((long long)t[u] * a.nac + c) * a.M + kp[u]];
-        }
+      for (int cc = 0; cc < 2; cc++)
 #pragma unroll
-      for (int u = 0; u < U; u++)
-        if (ok[u]) { acc[u].x = acc[u].x + X[u].x * sg[u]; acc[u].y = acc[u].y + X[u].y * sg[u]; }
+        for (int u = 0; u < U; u++)
+          if (ok[u] && c0 + cc < a.nac) {
+            X[cc][u] = a.Y[(((long long)frame * nsym + c0 + cc) * a.N + r[u]) * a.M + kp[u]];
+            sg[cc][u] = a.sgn[((long long)t[u] * a.nac + c0 + cc) * a.M + kp[u]];
+          }
+#pragma unroll
+      for (int cc = 0; cc < 2; cc++)
+#pragma unroll
+        for (int u = 0; u < U; u++)
+          if (ok[u] && c0 + cc < a.nac) { acc[u].x = acc[u].x + X[cc][u].x * sg[cc][u]; acc[u].y = acc[u].y + X[cc][u].y * sg[cc][u]; }
     }
 #pragma unroll
     for (int u = 0; u < U; u++)
