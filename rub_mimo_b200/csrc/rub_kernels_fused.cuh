@@ -239,11 +239,15 @@ __device__ __forceinline__ unsigned demap_one(cf z, float isig, const float *ref
   return c ^ ((c >> 1) & ~(1u << (MB - 1)));
 }
 
+template <int N> struct ErrWords;
+template <int N>
+__device__ __forceinline__ void flush_counts(const unsigned *eb, const unsigned *es, unsigned *cnt);
+
 template <int N, int MB>
 __device__ __forceinline__ void task_compute(const TaskRegs<N> &t, const ChainArgs &a, const float4 *y4,
                                              long long o, float *lp, unsigned char *bp, const DemapConst &lut,
                                              const float *refs, unsigned long long pol_stream,
-                                             unsigned txv, unsigned *cnt_s) {
+                                             unsigned txv, unsigned &ebw, unsigned &esw, int cshift) {
   constexpr int Q = 2 * MB;
   const int lane = threadIdx.x & 31;
   cf w0[N], w1[N], y0[N], y1[N];
@@ -286,10 +290,10 @@ __device__ __forceinline__ void task_compute(const TaskRegs<N> &t, const ChainAr
     }
   }
   if (a.tx_data) {
-    // warp-uniform address: ptxas turns each atomicAdd into REDUX.SUM + one ATOMS per warp
+    // per-lane packed counters (one byte per stream), reduced once per OFDM symbol by the caller
     const unsigned x = rx2 ^ txv;
-    atomicAdd(cnt_s, (unsigned)__popc(x));
-    atomicAdd(cnt_s + 1, (unsigned)((x & 0xffu) != 0u) + (unsigned)((x >> 8) != 0u));
+    ebw += (unsigned)__popc(x) << cshift;
+    esw += ((unsigned)((x & 0xffu) != 0u) + (unsigned)((x >> 8) != 0u)) << cshift;
   }
 }
 
@@ -356,6 +360,8 @@ __device__ __forceinline__ void detect_symbol(const FusedArgs &fa, TaskRegs<N> &
   const cf *Yl = buf + wc.koff;
   const unsigned char *txl = txs + wc.koff;   // transmitted symbols of this OFDM symbol, [stream][k] in smem
   TaskRegs<N> nxt;
+  static_assert(KPW * 2 * 8 <= 255, "a symbol's bit errors of one lane and stream fit a byte");
+  unsigned eb[ErrWords<N>::NW] = {}, es[ErrWords<N>::NW] = {};
 #pragma unroll
   for (int kb = 0; kb < KPW; kb++) {
     float4 y4[N];
@@ -377,7 +383,7 @@ __device__ __forceinline__ void detect_symbol(const FusedArgs &fa, TaskRegs<N> &
       task_compute<N, MB>(cur, a, y4, o, reinterpret_cast<float *>(slot) + lane * 2 * Q,
                           slot + fa.llr_stage_bytes + (lane >> 2) * Q, lut, refs, pol_stream,
                           a.tx_data ? (unsigned)*reinterpret_cast<const unsigned short *>(txl + s * M + kb * KSTEP) : 0u,
-                          cnt + 2 * s);
+                          eb[s >> 2], es[s >> 2], 8 * (s & 3));
       fence_async_smem();
       __syncwarp();
       if (lane == 0) {
@@ -389,6 +395,7 @@ __device__ __forceinline__ void detect_symbol(const FusedArgs &fa, TaskRegs<N> &
       if (it + 1 < KPW * N) cur = nxt;
     }
   }
+  if (a.tx_data) flush_counts<N>(eb, es, cnt);
 }
 
 template <int LOG2M, int N>
