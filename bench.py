@@ -54,10 +54,16 @@ def _peaks():
 
 
 def kernel_source_sha():
+    """Hash of the kernel sources with comments and white space removed: a comment edit does not change the
+    machine code and must not invalidate the stamp of profiles/traffic.json, any code edit does."""
+    import re
     h = hashlib.sha256()
     for n in KERNEL_SOURCES:
-        with open(os.path.join(ROOT, "rub_mimo_b200", "csrc", n), "rb") as f:
-            h.update(f.read())
+        with open(os.path.join(ROOT, "rub_mimo_b200", "csrc", n), "r") as f:
+            src = f.read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        src = re.sub(r"//[^\n]*", "", src)
+        h.update(re.sub(r"\s+", "", src).encode())
     return h.hexdigest()[:16]
 
 

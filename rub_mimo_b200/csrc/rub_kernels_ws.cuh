@@ -1,16 +1,18 @@
 // rub_kernels_ws.cuh — the fused receive kernel, warp specialised (one persistent CTA per SM):
 //
-//   FFT warps       NT threads (one warpgroup).  Payload symbols: in-place FFT of the N antennas in a
-//                   two-deep ring of landing buffers, stage by stage over the antennas, handed to the
-//                   detect warps through an mbarrier.  Training symbols never reach the detect warps:
-//                   they are transformed one antenna at a time in a small landing pair of their own
-//                   and the LS estimate is accumulated straight from the last stage's registers into
-//                   the frame's G scratch.  The training symbols of frame f+1 are interleaved with
-//                   the payload symbols of frame f, so the FFT load is even over time.
-//   detect warps    weights once per frame, then W*y -> gain -> slicer -> max-log LLR -> packed bits
-//                   -> error count per payload symbol, one symbol behind the FFT.  The last detect
-//                   warp to finish a symbol refills the ring slot it frees (TMA bulk loads of the
-//                   payload symbol two ahead, CP strip by address, completed on an mbarrier).
+//   FFT warps       NT threads (one warpgroup, 128 registers).  Payload symbols: in-place FFT of the N antennas
+//                   in a two-deep ring of landing slots, stage by stage over the antennas, handed to the detect
+//                   warps through an mbarrier.  Training symbols never reach the detect warps: they arrive one
+//                   antenna at a time in a landing row, are transformed in a work row, and the LS estimate is
+//                   accumulated straight from the last stage's registers into the frame's G scratch.  The
+//                   training symbols of frame f+1 are interleaved with the payload symbols of frame f (quota +
+//                   work-conserving test), so the FFT load is even over time.
+//   detect warps    16 warps, 88 registers.  Weights once per frame (written as task records: W, gain and
+//                   1/sigma^2 of one stream's 64 carriers, 2560 B contiguous), then per payload symbol
+//                   W*y -> gain -> slicer -> max-log LLR -> packed bits -> error count, one symbol behind the
+//                   FFT.  A warp fetches the record of its next task with one TMA bulk copy while it finishes
+//                   the current one; the last detect warp to finish a symbol refills the ring slot it frees (TMA
+//                   bulk loads of the payload symbol two ahead, CP strip by address, completed on an mbarrier).
 //
 // replacing framesync::execute_mimo_decode (mimo/framing.cc:535-589), the LS/invert part of
 // estimate_channel (:801-832) and the demod/count loop of mimo/main.cc:1403-1410.
@@ -22,8 +24,8 @@
 // arrival counter instead of CTA-wide barriers.  Both loops are kept small on purpose (rolled over
 // antennas / tasks): the SM has one 32 KB instruction cache for both roles and a single FFT warp
 // per scheduler hides no fetch latency.  Frame f+1 is estimated while frame f is detected: its LS
-// estimate goes to a scratch of its own (ordinary L2 policy), the W/gain/isig scratch that the detect
-// warps re-read D times per frame stays a single evict_last set per CTA.
+// estimate goes to a scratch of its own, the task records that the detect warps re-read D times per frame
+// stay a single evict_last set per CTA.  DESIGN.md 4.1 has the measurements behind each of these choices.
 #pragma once
 #include <type_traits>
 
