@@ -15,22 +15,41 @@ bool fused_has_instance(uint32_t l2, uint32_t N) {
   return false;
 }
 template <int LOG2M, int N>
-static cudaError_t prepare(uint32_t q, size_t *smem_out, int *occ) {
+static cudaError_t prepare(uint32_t q, size_t *smem_out, int *occ, int *variant) {
   using TR = FusedTraits<LOG2M, N>;
+  *variant = 0;
+  if (TR::HAS_WTMA && !getenv("RUB_FUSED_NO_WTMA")) {
+    // the TMA-record variant, if it keeps the occupancy the classic one is built for
+    const size_t sm = TR::smem_bytes((int)q, true);
+    int o = 0;
+    if (cudaFuncSetAttribute(k_rx_fused<LOG2M, N, TR::HAS_WTMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_rx_fused<LOG2M, N, TR::HAS_WTMA>, TR::THREADS, sm) == cudaSuccess &&
+        o >= TR::MIN_CTAS) {
+      *smem_out = sm; *occ = o; *variant = 1;
+      return cudaSuccess;
+    }
+    cudaGetLastError();
+  }
   const size_t smem = TR::smem_bytes((int)q);
   cudaError_t e = cudaFuncSetAttribute(k_rx_fused<LOG2M, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   *smem_out = smem;
   return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_rx_fused<LOG2M, N>, TR::THREADS, smem);
 }
-cudaError_t fused_prepare(uint32_t l2, uint32_t N, uint32_t q, size_t *smem, int *occ) {
-#define X(L, NN) if (l2 == L && N == NN) return prepare<L, NN>(q, smem, occ);
+cudaError_t fused_prepare(uint32_t l2, uint32_t N, uint32_t q, size_t *smem, int *occ, int *variant) {
+#define X(L, NN) if (l2 == L && N == NN) return prepare<L, NN>(q, smem, occ, variant);
   RUB_FUSED_LIST(X)
 #undef X
   return cudaErrorInvalidValue;
 }
-void fused_launch(uint32_t l2, uint32_t N, int grid, size_t smem, cudaStream_t st, const FusedArgs &fa, const DemapConst &dc) {
-#define X(L, NN) if (l2 == L && N == NN) { k_rx_fused<L, NN><<<grid, FusedTraits<L, NN>::THREADS, smem, st>>>(fa, dc); return; }
+template <int LOG2M, int N>
+static void launch_fused(int grid, size_t smem, cudaStream_t st, const FusedArgs &fa, const DemapConst &dc, int variant) {
+  using TR = FusedTraits<LOG2M, N>;
+  if (variant && TR::HAS_WTMA) k_rx_fused<LOG2M, N, TR::HAS_WTMA><<<grid, TR::THREADS, smem, st>>>(fa, dc);
+  else k_rx_fused<LOG2M, N><<<grid, TR::THREADS, smem, st>>>(fa, dc);
+}
+void fused_launch(uint32_t l2, uint32_t N, int grid, size_t smem, cudaStream_t st, const FusedArgs &fa, const DemapConst &dc, int variant) {
+#define X(L, NN) if (l2 == L && N == NN) { launch_fused<L, NN>(grid, smem, st, fa, dc, variant); return; }
   RUB_FUSED_LIST(X)
 #undef X
 }

@@ -191,9 +191,23 @@ struct FusedTraits {
   static constexpr int TW_SMEM_ELEMS = TW_SMEM ? FftTw<LOG2M>::TOTAL : 0;
   static_assert(NT % 32 == 0, "fused path needs NT to be whole warps");
   static_assert(KPW >= 1 && KPW * N * NWARPS == TASKS && (TPW % 2) == 0, "task split");
-  static size_t smem_bytes(int q) {
-    return (size_t)2 * BUF_ELEMS * sizeof(cf) + (size_t)NWARPS * 2 * (256 * q + 64) +
-           (size_t)TW_SMEM_ELEMS * sizeof(cf) + (size_t)2 * N * M /* tx_data */ + 64 /* mbarriers */ + 8 * N * 2 + 64;
+  // WTMA variant (two-stream instances): W, gain and 1/sigma^2 of a detection task come as one TMA record into a
+  // two-deep per-warp ring, two tasks ahead of their use; it pays for the ring with the second LLR staging slot and
+  // the shared-memory copy of the stage twiddles (read through L1 instead)
+  // (measured: 2-4 % faster at M = 1024 / 2048; slower at 512, where a CTA is two warps, and at 4096, whose 32 KB of
+  // stage twiddles then come through L1)
+  static constexpr bool HAS_WTMA = N == 2 && (LOG2M == 10 || LOG2M == 11);
+  static constexpr int KB = M / 64;                 // 64-carrier blocks per symbol
+  static constexpr int REC = N * 64 + 64;           // task record in cf units: W[rx][64], gain[64] f32, isig[64] f32
+  static size_t smem_bytes(int q, bool wtma = false) {
+    return (size_t)2 * BUF_ELEMS * sizeof(cf) + (size_t)NWARPS * (wtma ? 1 : 2) * (256 * q + 64) +
+           (wtma ? (size_t)NWARPS * 2 * REC * sizeof(cf) + (size_t)NWARPS * 2 * 8 : (size_t)TW_SMEM_ELEMS * sizeof(cf)) +
+           (size_t)2 * N * M /* tx_data */ + 64 /* mbarriers */ + 8 * N * 2 + 64;
+  }
+  // position (cf index) of W[e = stream * N + rx][k] in the per-CTA scratch: classic [e][k] or task records
+  template <bool WTMA>
+  RUB_HD static int wpos(int e, int k) {
+    return WTMA ? ((e / N) * KB + (k >> 6)) * REC + (e % N) * 64 + (k & 63) : e * M + k;
   }
 };
 
@@ -212,6 +226,11 @@ struct WarpCtx {
   int stage_stride;
   int koff;              // first carrier of this lane: warp*64 + 2*lane
   int kw;                // first carrier of this warp (warp-uniform)
+  // WTMA variant: this warp's two-deep record ring, its mbarriers and the number of records consumed so far
+  cf *wring;
+  unsigned long long *wrdy;
+  const cf *Wrec;        // the CTA's record scratch
+  unsigned wn;
 };
 
 template <int N, int M>
@@ -345,12 +364,23 @@ __device__ __forceinline__ void flush_counts(const unsigned *eb, const unsigned 
 // detection of one payload OFDM symbol by the whole CTA; `cur` already holds task 0.
 // A warp walks KPW blocks of 64 carriers; for each block it reads Y once (N x 16 B per lane) and
 // serves the N streams one after the other.
-template <int LOG2M, int N, int MB>
-__device__ __forceinline__ void detect_symbol(const FusedArgs &fa, TaskRegs<N> &cur, const WarpCtx &wc,
+// record of task number `task` of this warp (stream task % N, block warp + (task / N) * NWARPS) -> ring slot
+// `slot` (one lane)
+template <int LOG2M, int N>
+__device__ __forceinline__ void issue_record(const WarpCtx &wc, int warp, int task, int slot, unsigned long long pol_keep) {
+  using TR = FusedTraits<LOG2M, N>;
+  const int s = task % N, blk = warp + (task / N) * TR::NWARPS;
+  unsigned long long *bar = wc.wrdy + slot;
+  mbar_expect_tx(bar, (unsigned)(TR::REC * sizeof(cf)));
+  bulk_load(wc.wring + (size_t)slot * TR::REC, wc.Wrec + (size_t)(s * TR::KB + blk) * TR::REC, (unsigned)(TR::REC * sizeof(cf)), bar, pol_keep);
+}
+
+template <int LOG2M, int N, int MB, bool WTMA>
+__device__ __forceinline__ void detect_symbol(const FusedArgs &fa, TaskRegs<N> &cur, WarpCtx &wc,
                                               const cf *buf, const unsigned char *txs, long long symbase,
                                               const DemapConst &lut,
                                               const float *refs, unsigned long long pol_keep,
-                                              unsigned long long pol_stream, unsigned *cnt) {
+                                              unsigned long long pol_stream, unsigned *cnt, bool more_symbols) {
   using TR = FusedTraits<LOG2M, N>;
   constexpr int M = TR::M, PAD = TR::PAD, KPW = TR::KPW, KSTEP = TR::KSTEP, Q = 2 * MB;
   const ChainArgs &a = fa.a;
@@ -371,19 +401,29 @@ __device__ __forceinline__ void detect_symbol(const FusedArgs &fa, TaskRegs<N> &
     for (int s = 0; s < N; s++) {
       constexpr int dummy = 0; (void)dummy;
       const int it = kb * N + s;
-      if (it + 1 < KPW * N) {
+      if (WTMA) {
+        // this task's record has landed in ring slot wn & 1 (requested two tasks ago)
+        const int rs = (int)(wc.wn & 1u);
+        mbar_wait_parked(wc.wrdy + rs, (wc.wn >> 1) & 1u);
+        const cf *rec = wc.wring + (size_t)rs * TR::REC;
+#pragma unroll
+        for (int r = 0; r < N; r++) cur.w[r] = *reinterpret_cast<const float4 *>(rec + r * 64 + 2 * lane);
+        cur.g = *reinterpret_cast<const float2 *>(reinterpret_cast<const float *>(rec + N * 64) + 2 * lane);
+        cur.is = *reinterpret_cast<const float2 *>(reinterpret_cast<const float *>(rec + N * 64) + 64 + 2 * lane);
+      } else if (it + 1 < KPW * N) {
         const int sn = (s + 1) % N, kn = (s + 1 == N) ? kb + 1 : kb;
         task_load<N, M>(nxt, wc, sn, kn * KSTEP, pol_keep);
       }
-      // the bulk store issued two tasks ago from this staging slot must have drained
-      if (lane == 0) bulk_wait_read<1>();
+      // the bulk store issued from this staging slot (two tasks ago; WTMA: the previous task) must have drained
+      if (lane == 0) { if (WTMA) bulk_wait_read<0>(); else bulk_wait_read<1>(); }
       __syncwarp();
       const long long o = obase + (long long)s * DM + kb * KSTEP;
-      unsigned char *slot = wc.slot0 + (it & 1) * wc.stage_stride;
+      unsigned char *slot = wc.slot0 + (WTMA ? 0 : (it & 1) * wc.stage_stride);
       task_compute<N, MB>(cur, a, y4, o, reinterpret_cast<float *>(slot) + lane * 2 * Q,
                           slot + fa.llr_stage_bytes + (lane >> 2) * Q, lut, refs, pol_stream,
                           a.tx_data ? (unsigned)*reinterpret_cast<const unsigned short *>(txl + s * M + kb * KSTEP) : 0u,
                           eb[s >> 2], es[s >> 2], 8 * (s & 3));
+      // (the proxy fence also waits for this lane's reads of the record: the record two tasks ahead may land there)
       fence_async_smem();
       __syncwarp();
       if (lane == 0) {
@@ -391,14 +431,17 @@ __device__ __forceinline__ void detect_symbol(const FusedArgs &fa, TaskRegs<N> &
         if (a.llr) bulk_store(a.llr + ob * Q, slot, (unsigned)(64 * Q * 4), pol_stream);
         if (a.bits) bulk_store(a.bits + (ob >> 3) * Q, slot + fa.llr_stage_bytes, (unsigned)(8 * Q), pol_stream);
         bulk_commit();
+        if (WTMA && (it + 2 < KPW * N || more_symbols))
+          issue_record<LOG2M, N>(wc, (int)(threadIdx.x >> 5), (it + 2) % (KPW * N), (int)(wc.wn & 1u), pol_keep);
       }
-      if (it + 1 < KPW * N) cur = nxt;
+      if (WTMA) wc.wn++;
+      else if (it + 1 < KPW * N) cur = nxt;
     }
   }
   if (a.tx_data) flush_counts<N>(eb, es, cnt);
 }
 
-template <int LOG2M, int N>
+template <int LOG2M, int N, bool WTMA = false>
 __global__ void __launch_bounds__(FusedTraits<LOG2M, N>::THREADS, FusedTraits<LOG2M, N>::MIN_CTAS) k_rx_fused(FusedArgs fa, DemapConst lutp) {
   using TR = FusedTraits<LOG2M, N>;
   using FF = Fft<LOG2M>;
@@ -411,10 +454,12 @@ __global__ void __launch_bounds__(FusedTraits<LOG2M, N>::THREADS, FusedTraits<LO
   cf *buf1 = buf0 + TR::BUF_ELEMS;
   unsigned char *stage_base = reinterpret_cast<unsigned char *>(buf1 + TR::BUF_ELEMS);
   const int stage_stride = fa.llr_stage_bytes + 64;  // llr block followed by 64 B of packed bits
-  cf *tw_s = reinterpret_cast<cf *>(stage_base + (size_t)NWARPS * 2 * stage_stride);  // stage twiddles, copied once
-  unsigned char *txbuf = reinterpret_cast<unsigned char *>(tw_s + TR::TW_SMEM_ELEMS);  // [2][N][M] tx symbols
-  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(txbuf + 2 * N * M);  // full[2], empty[2]
-  unsigned *cnt = reinterpret_cast<unsigned *>(mbar + 4);  // [N][2] bit errors, symbol errors
+  // classic: two LLR staging slots per warp, then the stage twiddles; WTMA: one slot per warp, then the record rings
+  cf *tw_s = reinterpret_cast<cf *>(stage_base + (size_t)NWARPS * (WTMA ? 1 : 2) * stage_stride);  // stage twiddles, copied once
+  cf *rings = tw_s;                                                                                  // [NWARPS][2][REC] (WTMA)
+  unsigned char *txbuf = reinterpret_cast<unsigned char *>(WTMA ? rings + (size_t)NWARPS * 2 * TR::REC : tw_s + TR::TW_SMEM_ELEMS);  // [2][N][M] tx symbols
+  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(txbuf + 2 * N * M);  // full[2], empty[2], WTMA: + wrdy[NWARPS][2]
+  unsigned *cnt = reinterpret_cast<unsigned *>(mbar + 4 + (WTMA ? NWARPS * 2 : 0));  // [N][2] bit errors, symbol errors
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform for the compiler
@@ -423,14 +468,18 @@ __global__ void __launch_bounds__(FusedTraits<LOG2M, N>::THREADS, FusedTraits<LO
   const int q = a.q;
   const unsigned long long pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
 
-  for (int i = tid; i < TR::TW_SMEM_ELEMS; i += THREADS) tw_s[i] = a.tw[i];
-  const cf *tws = TR::TW_SMEM ? tw_s : a.tw;
+  constexpr bool TW_S = TR::TW_SMEM && !WTMA;
+  if (TW_S)
+    for (int i = tid; i < TR::TW_SMEM_ELEMS; i += THREADS) tw_s[i] = a.tw[i];
+  const cf *tws = TW_S ? tw_s : a.tw;
   if (tid < 2 * N) cnt[tid] = 0;
   if (tid == 0) {
     mbar_init(&mbar[0], 1);
     mbar_init(&mbar[1], 1);
     mbar_init(&mbar[2], NWARPS);
     mbar_init(&mbar[3], NWARPS);
+    if (WTMA)
+      for (int i = 0; i < NWARPS * 2; i++) mbar_init(&mbar[4 + i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
   }
@@ -438,7 +487,7 @@ __global__ void __launch_bounds__(FusedTraits<LOG2M, N>::THREADS, FusedTraits<LO
 
   const int nf_cta = (a.n_frames - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int total = nf_cta * nsym;  // flat (frame, symbol) sequence of this CTA
-  cf *Wc = fa.scratchW + (size_t)blockIdx.x * N * N * M;
+  cf *Wc = fa.scratchW + (size_t)blockIdx.x * (WTMA ? N * TR::KB * TR::REC : N * N * M);
   float *gc = fa.scratchG + (size_t)blockIdx.x * 2 * N * M, *ic = gc + (size_t)N * M;
   const unsigned sym_bytes = (unsigned)(M * sizeof(cf));
 
@@ -448,8 +497,12 @@ __global__ void __launch_bounds__(FusedTraits<LOG2M, N>::THREADS, FusedTraits<LO
   wc.koff = wc.kw + 2 * lane;
   wc.Wp = Wc + wc.koff;
   wc.gp = gc + wc.koff;
-  wc.slot0 = stage_base + (size_t)(warp * 2) * stage_stride;
+  wc.slot0 = stage_base + (size_t)(warp * (WTMA ? 1 : 2)) * stage_stride;
   wc.stage_stride = stage_stride;
+  wc.wring = rings + (size_t)warp * 2 * TR::REC;
+  wc.wrdy = mbar + 4 + warp * 2;
+  wc.Wrec = Wc;
+  wc.wn = 0;
   float refs[4];  // liquid ref[k] = 2^k * alpha, most significant first
 #pragma unroll
   for (int i = 0; i < 4; i++) refs[i] = (i < q / 2) ? (float)(1u << (q / 2 - 1 - i)) * lutp.alpha : 0.f;
@@ -489,7 +542,7 @@ __global__ void __launch_bounds__(FusedTraits<LOG2M, N>::THREADS, FusedTraits<LO
     auto prefetch_task0 = [&]() {
       // W/gain/isig/tx_data of this warp's first detection task, issued before the last FFT
       // stage so the L2 latency hides behind it
-      if (payload) {
+      if (payload && !WTMA) {
         task_load<N, M>(cur, wc, 0, 0, pol_keep);
       }
     };
@@ -519,7 +572,7 @@ __global__ void __launch_bounds__(FusedTraits<LOG2M, N>::THREADS, FusedTraits<LO
       if (PL::NSTG == 2) prefetch_task0();
       FF::S1::template load<true>(ft, mine, v);
       group_sync<NT>(1 + ant);
-      FF::S1::template compute<TR::TW_SMEM>(ft, v, tws + TW::OFF1);
+      FF::S1::template compute<TW_S>(ft, v, tws + TW::OFF1);
       if (PL::NSTG == 2) {
         FF::S1::template store<false, true>(ft, v, mine, scale);
       } else {
@@ -528,7 +581,7 @@ __global__ void __launch_bounds__(FusedTraits<LOG2M, N>::THREADS, FusedTraits<LO
         prefetch_task0();
         FF::S2::template load<true>(ft, mine, v);
         group_sync<NT>(1 + ant);
-        FF::S2::template compute<TR::TW_SMEM>(ft, v, tws + TW::OFF2);
+        FF::S2::template compute<TW_S>(ft, v, tws + TW::OFF2);
         FF::S2::template store<false, true>(ft, v, mine, scale);
       }
     }
@@ -546,7 +599,7 @@ __global__ void __launch_bounds__(FusedTraits<LOG2M, N>::THREADS, FusedTraits<LO
       for (int i = 0; i < LS_IT; i++) {
         const int e = tid + i * THREADS, r = e / (M / 2), k = 2 * (e % (M / 2));
         if (c == 0) { const float d = (q1 && r == t) ? 1.0f : 0.0f; accv[i] = make_float4(d, 0.f, d, 0.f); }
-        else accv[i] = ld_hint4(Wc + (size_t)(r * N + t) * M + k, pol_keep);
+        else accv[i] = ld_hint4(Wc + TR::template wpos<WTMA>(r * N + t, k), pol_keep);
       }
 #pragma unroll
       for (int i = 0; i < LS_IT; i++) {
@@ -556,7 +609,7 @@ __global__ void __launch_bounds__(FusedTraits<LOG2M, N>::THREADS, FusedTraits<LO
         float4 acc = accv[i];
         acc.x = acc.x + x.x * sg.x; acc.y = acc.y + x.y * sg.x;
         acc.z = acc.z + x.z * sg.y; acc.w = acc.w + x.w * sg.y;
-        st_hint4(Wc + (size_t)(r * N + t) * M + k, acc, pol_keep);
+        st_hint4(Wc + TR::template wpos<WTMA>(r * N + t, k), acc, pol_keep);
       }
       release_buf();
       if (sym == a.T - 1) {
@@ -567,7 +620,7 @@ __global__ void __launch_bounds__(FusedTraits<LOG2M, N>::THREADS, FusedTraits<LO
           float gain[N], isig[N];
 #pragma unroll
           for (int e = 0; e < N * N; e++) {
-            const float2 t2 = ld_hint2(Wc + (size_t)e * M + k, pol_keep);
+            const float2 t2 = ld_hint2(Wc + TR::template wpos<WTMA>(e, k), pol_keep);
             G[e] = cscale(mk(t2.x, t2.y), a.s_ls);
           }
           if (a.G) {
@@ -576,15 +629,33 @@ __global__ void __launch_bounds__(FusedTraits<LOG2M, N>::THREADS, FusedTraits<LO
           }
           compute_weights<N>(fa.wm, G, W, gain, isig);
 #pragma unroll
-          for (int e = 0; e < N * N; e++) st_hint2(Wc + (size_t)e * M + k, make_float2(W[e].x, W[e].y), pol_keep);
+          for (int e = 0; e < N * N; e++) st_hint2(Wc + TR::template wpos<WTMA>(e, k), make_float2(W[e].x, W[e].y), pol_keep);
 #pragma unroll
-          for (int s = 0; s < N; s++) { st_hint1(gc + (size_t)s * M + k, gain[s], pol_keep); st_hint1(ic + (size_t)s * M + k, isig[s], pol_keep); }
+          for (int s = 0; s < N; s++) {
+            if (WTMA) {  // gain and isig ride in the task record
+              float *rec = reinterpret_cast<float *>(Wc + (size_t)(s * TR::KB + (k >> 6)) * TR::REC + N * 64);
+              st_hint1(rec + (k & 63), gain[s], pol_keep);
+              st_hint1(rec + 64 + (k & 63), isig[s], pol_keep);
+            } else {
+              st_hint1(gc + (size_t)s * M + k, gain[s], pol_keep);
+              st_hint1(ic + (size_t)s * M + k, isig[s], pol_keep);
+            }
+          }
+        }
+        if (WTMA) {  // the records are read through the async proxy (TMA)
+          __threadfence();
+          asm volatile("fence.proxy.async;" ::: "memory");
         }
         __syncthreads();  // W complete before any warp prefetches it for the first payload symbol
+        if (WTMA && lane == 0) {
+          // the first two task records of the frame; every later one is requested two tasks ahead by detect_symbol
+          issue_record<LOG2M, N>(wc, warp, 0, (int)(wc.wn & 1u), pol_keep);
+          issue_record<LOG2M, N>(wc, warp, 1, (int)((wc.wn + 1) & 1u), pol_keep);
+        }
       }
     } else {
       // ---------------- detect + demap + count ----------------
-#define DETECT(MBV) detect_symbol<LOG2M, N, MBV>(fa, cur, wc, buf, txbuf + (g & 1) * N * M, symbase, lutp, refs, pol_keep, pol_stream, cnt)
+#define DETECT(MBV) detect_symbol<LOG2M, N, MBV, WTMA>(fa, cur, wc, buf, txbuf + (g & 1) * N * M, symbase, lutp, refs, pol_keep, pol_stream, cnt, sym + 1 < nsym)
       switch (q) {
         case 2: DETECT(1); break;
         case 4: DETECT(2); break;

@@ -9,8 +9,9 @@ namespace rub {
 
 // monolithic fused kernel (rub_kernels_fused.cuh)
 bool fused_has_instance(uint32_t log2M, uint32_t N);
-cudaError_t fused_prepare(uint32_t log2M, uint32_t N, uint32_t q, size_t *smem, int *ctas_per_sm);
-void fused_launch(uint32_t log2M, uint32_t N, int grid, size_t smem, cudaStream_t st, const FusedArgs &fa, const DemapConst &dc);
+// variant 1 = W / gain / isig as TMA task records (two-stream instances, when the shared memory allows)
+cudaError_t fused_prepare(uint32_t log2M, uint32_t N, uint32_t q, size_t *smem, int *ctas_per_sm, int *variant);
+void fused_launch(uint32_t log2M, uint32_t N, int grid, size_t smem, cudaStream_t st, const FusedArgs &fa, const DemapConst &dc, int variant);
 // warp-specialised fused kernel (rub_kernels_ws.cuh)
 bool ws_has_instance(uint32_t log2M, uint32_t N);
 cudaError_t ws_prepare(uint32_t log2M, uint32_t N, uint32_t q, size_t *smem, int *ctas_per_sm);

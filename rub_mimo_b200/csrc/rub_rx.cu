@@ -96,6 +96,7 @@ struct rub_rx {
   unsigned char *d_sgn8 = nullptr;  // warp-specialised kernel: packed access-code signs
   std::vector<float> sgn_host;      // access-code signs [tx][code][M]
   int fused_grid = 0;
+  int fused_variant = 0;  // monolithic fused kernel: 1 = TMA task records (rub_launch.h)
   bool ws = false;  // the warp-specialised fused kernel (rub_kernels_ws.cuh) serves this configuration
   size_t fused_smem = 0;
   bool fused_ready = false;
@@ -131,7 +132,7 @@ static rub_status fused_prepare_dispatch(rub_rx *h, size_t *smem, int *grid) {
     ce = ws_prepare(h->h.log2M, h->h.N, h->h.q, smem, &occ);
     if (ce != cudaSuccess || occ < 1) { cudaGetLastError(); h->ws = false; }  // e.g. 256-QAM staging does not fit: monolithic kernel
   }
-  if (!h->ws) ce = fused_prepare(h->h.log2M, h->h.N, h->h.q, smem, &occ);
+  if (!h->ws) ce = fused_prepare(h->h.log2M, h->h.N, h->h.q, smem, &occ, &h->fused_variant);
   if (ce != cudaSuccess || occ < 1) {
     cudaGetLastError();
     set_error("no fused kernel fits this configuration (shared memory %zu B)", *smem);
@@ -142,7 +143,7 @@ static rub_status fused_prepare_dispatch(rub_rx *h, size_t *smem, int *grid) {
 }
 static void fused_launch_dispatch(rub_rx *h, int grid, size_t smem, const FusedArgs &fa) {
   if (h->ws) ws_launch(h->h.log2M, h->h.N, grid, smem, h->stream, fa, h->lut);
-  else fused_launch(h->h.log2M, h->h.N, grid, smem, h->stream, fa, h->lut);
+  else fused_launch(h->h.log2M, h->h.N, grid, smem, h->stream, fa, h->lut, h->fused_variant);
 }
 
 // is the fused kernel applicable to this configuration + call?
@@ -460,8 +461,8 @@ static rub_status run_fused(rub_rx *h, const ChainArgs &a, uint32_t n_frames, bo
     h->fused_grid = grid;
     h->fused_smem = smem;
     // per-CTA scratch: G -> W in place, gain, isig (re-read D times per frame: L2 resident)
-    // (the warp-specialised kernel keeps W, gain and isig together as task records in the first buffer)
-    CUDA_TRY(cudaMalloc(&h->d_fW, (size_t)grid * (c.N * c.N * c.M * sizeof(cf) + (h->ws ? 2 * c.N * c.M * sizeof(float) : 0))));
+    // (the kernels that fetch W by TMA keep W, gain and isig together as task records in the first buffer)
+    CUDA_TRY(cudaMalloc(&h->d_fW, (size_t)grid * (c.N * c.N * c.M * sizeof(cf) + 2 * c.N * c.M * sizeof(float))));
     CUDA_TRY(cudaMalloc(&h->d_fG, (size_t)grid * 2 * c.N * c.M * sizeof(float)));
     if (h->ws) {
       // the warp-specialised kernel estimates frame f+1 while frame f is detected

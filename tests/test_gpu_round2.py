@@ -129,3 +129,18 @@ def test_ws_kernel_frame_and_symbol_count_edges(D, nac, cp, frames):
     per = np.stack([oracle_run(cfg, S1, iq_u[i:i + 1], tx_u[i:i + 1])["counters"] for i in range(U)])
     assert np.array_equal(rx.read_counters(), 2 * per[idx].sum(axis=0))
     rx.close()
+
+
+@pytest.mark.parametrize("M,cp", [(1024, 72), (2048, 152)])
+def test_two_stream_fused_kernel_variants(M, cp, monkeypatch):
+    """2x2 at M = 1024 / 2048 runs the monolithic fused kernel with W/gain/isig as TMA task records; the classic
+    variant (register prefetch) stays selectable and both agree with the oracle bit for bit."""
+    cfg = rub.Config(M=M, cp_len=cp, num_streams=2, num_access_codes=3, num_data_symbols=5, modulation=rub.MOD_QAM16,
+                     detector=rub.DET_ZF)
+    cfg, S1, iq, tx = make_case(cfg, 9, seed=M, n_taps=3, snr_db=24.0)
+    for no_wtma in (False, True):
+        if no_wtma:
+            monkeypatch.setenv("RUB_FUSED_NO_WTMA", "1")
+        else:
+            monkeypatch.delenv("RUB_FUSED_NO_WTMA", raising=False)
+        _run_masks(cfg, S1, iq, tx, rub.PATH_FUSED, MASKS[:3], kernel="k_rx_fused")
