@@ -105,13 +105,19 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
-    def stop(self):
+    def mark(self):
+        """Number of samples taken so far (to delimit the timed region inside the sampler's lifetime)."""
+        return len(self.rows)
+
+    def stop(self, first=0, last=None):
+        """Statistics over the samples [first, last) (default: all)."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+        if self.proc.poll() is None:
+            time.sleep(0.15)
+            self.proc.terminate()
         sm, mx, pw, reasons = [], [], [], set()
-        for r in self.rows:
+        for r in self.rows[first:last]:
             p = [x.strip() for x in r.split(",")]
             if len(p) < 8:
                 continue
@@ -452,6 +458,7 @@ def run_ours(args):
     round_ms, step_ms = [], []
     launches0 = rx.launch_count
     n_rounds = 0
+    mark0 = sampler.mark()
     while True:
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
         torch.cuda.synchronize()
@@ -477,6 +484,8 @@ def run_ours(args):
             dist.broadcast(stop, src=0)
         if stop.item() > 0:
             break
+    time.sleep(0.06)              # let the 50 ms sampler catch the tail of the last round
+    mark1 = sampler.mark()
     launches = (rx.launch_count - launches0) // n_rounds
     ms = float(np.median(round_ms))
     local_counters = rx.read_counters()
@@ -548,7 +557,12 @@ def run_ours(args):
         if old_aff:
             os.sched_setaffinity(0, old_aff)
 
-    clocks = sampler.stop() if rank == 0 else None   # covers the timed rounds, the kernel loop and e2e
+    # clocks / throttle reasons of the TIMED rounds (the samples taken between their first and last step); the
+    # whole run (kernel loop, e2e, probe: mostly an idle GPU) is kept beside it
+    clocks = None
+    if rank == 0:
+        clocks = sampler.stop(mark0, mark1)
+        clocks["whole_run"] = sampler.stop()
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
